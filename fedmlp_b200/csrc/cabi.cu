@@ -1,0 +1,18 @@
+// cabi.cu — ABI version / status strings / device queries of libfedmlp_b200.
+#include "common.cuh"
+
+extern "C" int fmlp_abi_version(void) { return FMLP_ABI_VERSION; }
+
+extern "C" const char* fmlp_status_string(int code) {
+    switch (code) {
+        case FMLP_OK: return "ok";
+        case FMLP_ERR_BAD_ARG: return "fedmlp_b200: bad argument (null pointer, negative size, or K/S/C out of range)";
+        case FMLP_ERR_UNSUPPORTED: return "fedmlp_b200: unsupported shape or alignment";
+        case FMLP_ERR_WORKSPACE: return "fedmlp_b200: workspace too small";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "fedmlp_b200: unknown status";
+}
+
+extern "C" int fmlp_sm_count(void) { return fmlp::sm_count(); }

@@ -1,0 +1,316 @@
+// loss.cu — K4: FedMLP training losses, forward value + gradient w.r.t. the logits in one launch.
+//
+// Replaces the op chains at utils/local_training.py:933-963 (stage 1) and :1171-1188 (stage 2)
+// together with utils/FedNoRo.py:16-22 (LogitAdjust_Multilabel == F.binary_cross_entropy on
+// probabilities) and the autograd graph torch builds behind them (~30 forward + ~40 backward
+// element-wise launches on [32, C] tensors).  Everything is evaluated with the formulas ATen
+// uses, in ATen's operation order, so the gradient agrees with autograd to the last ulp or two:
+//   forward   BCE(p,y) = (y-1)*max(log1p(-p),-100) - y*max(log(p),-100)
+//   backward  dBCE/dp  = g*(p-y) / max((1-p)*p, 1e-12)         (binary_cross_entropy_backward)
+//             dMSE/dp  = (2*(p-t))*g                             (mse_loss_backward, reduction none)
+//             dp/dz    = (g*(1-p))*p                             (sigmoid_backward)
+// The kernels are launched cooperatively: phase boundaries (stage-2 denominator, final loss
+// reduction) are grid barriers, per-CTA partials are combined in CTA order -> deterministic,
+// no atomics, no pre-zeroed workspace.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fmlp {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossUnroll = 4;
+constexpr int kLossMaxGrid = 2048;  // workspace: 4 arrays of kLossMaxGrid 32-bit words
+
+__device__ __forceinline__ float bce_fwd(float p, float y) {
+    return __fsub_rn(__fmul_rn(__fsub_rn(y, 1.f), fmaxf(log1pf(-p), -100.f)),
+                     __fmul_rn(y, fmaxf(logf(p), -100.f)));
+}
+__device__ __forceinline__ float bce_bwd(float g, float p, float y) {
+    return __fdiv_rn(__fmul_rn(g, __fsub_rn(p, y)), fmaxf(__fmul_rn(__fsub_rn(1.f, p), p), 1e-12f));
+}
+__device__ __forceinline__ float mse_bwd(float g, float p, float t) {
+    return __fmul_rn(__fmul_rn(2.f, __fsub_rn(p, t)), g);
+}
+__device__ __forceinline__ float sigmoid_bwd(float g, float p) {
+    return __fmul_rn(__fmul_rn(g, __fsub_rn(1.f, p)), p);
+}
+
+// Sum `v` over the CTA; valid in thread 0.
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+        r = warp_sum(r);
+    }
+    return r;
+}
+__device__ __forceinline__ int block_sum_i(int v, int* s_red) {
+    v = warp_sum_i(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0;
+        r = warp_sum_i(r);
+    }
+    return r;
+}
+
+struct Loss1Args {
+    const float *z1, *z2, *z3, *z4, *y;
+    float *loss, *dz1, *dz2;
+    float* ws;
+    int64_t n;  // B*C
+    int C;
+    uint32_t active, missing;
+    float den_sup, den_dis;  // (float)(bs*A), (float)(bs*M)
+};
+
+__global__ void __launch_bounds__(kLossThreads) loss_stage1_kernel(const __grid_constant__ Loss1Args a) {
+    __shared__ float s_red[32];
+    float sup = 0.f, dis = 0.f;
+    // upstream gradients of the two sums (autograd: grad/den, then /2)
+    const float g_sup = __fmul_rn(__fdiv_rn(1.f, a.den_sup), 0.5f);
+    const float g_dis = __fmul_rn(__fdiv_rn(1.f, a.den_dis), 0.5f);
+    const int64_t stride = (int64_t)gridDim.x * kLossThreads * kLossUnroll;
+    for (int64_t base = (int64_t)blockIdx.x * kLossThreads * kLossUnroll + threadIdx.x; base < a.n; base += stride) {
+        float v1[kLossUnroll], v2[kLossUnroll], v3[kLossUnroll], v4[kLossUnroll], vy[kLossUnroll];
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int64_t e = base + (int64_t)u * kLossThreads;
+            const bool ok = e < a.n;
+            v1[u] = ok ? a.z1[e] : 0.f; v2[u] = ok ? a.z2[e] : 0.f;
+            v3[u] = ok ? a.z3[e] : 0.f; v4[u] = ok ? a.z4[e] : 0.f;
+            vy[u] = ok ? a.y[e] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int64_t e = base + (int64_t)u * kLossThreads;
+            if (e >= a.n) continue;
+            const int c = (int)(e % a.C);
+            const float p1 = sigmoid_ref(v1[u]), p2 = sigmoid_ref(v2[u]);
+            float d1 = 0.f, d2 = 0.f;
+            if ((a.active >> c) & 1u) {
+                // (loss_sup1 + loss_sup2) / 2.   (:952-954)
+                sup += __fmul_rn(__fadd_rn(bce_fwd(p1, vy[u]), bce_fwd(p2, vy[u])), 0.5f);
+                d1 = sigmoid_bwd(bce_bwd(g_sup, p1, vy[u]), p1);
+                d2 = sigmoid_bwd(bce_bwd(g_sup, p2, vy[u]), p2);
+            } else if ((a.missing >> c) & 1u) {
+                const float p3 = sigmoid_ref(v3[u]), p4 = sigmoid_ref(v4[u]);
+                const float e1 = __fsub_rn(p1, p3), e2 = __fsub_rn(p2, p4);
+                // (loss_dis1 + loss_dis2) / 2.   (:949-951)
+                dis += __fmul_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), 0.5f);
+                d1 = sigmoid_bwd(mse_bwd(g_dis, p1, p3), p1);
+                d2 = sigmoid_bwd(mse_bwd(g_dis, p2, p4), p2);
+            }
+            a.dz1[e] = d1;
+            a.dz2[e] = d2;
+        }
+    }
+    const float bs_sup = block_sum(sup, s_red);
+    const float bs_dis = block_sum(dis, s_red);
+    if (threadIdx.x == 0) { a.ws[blockIdx.x] = bs_sup; a.ws[kLossMaxGrid + blockIdx.x] = bs_dis; }
+    cg::this_grid().sync();
+    if (blockIdx.x == 0) {
+        float ts = 0.f, td = 0.f;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kLossThreads) { ts += a.ws[b]; td += a.ws[kLossMaxGrid + b]; }
+        ts = block_sum(ts, s_red);
+        td = block_sum(td, s_red);
+        if (threadIdx.x == 0) {
+            // loss = loss_sup + 0.0*loss_unsup + loss_dis   (:956-963); the 0.0* term is +0
+            const float l_sup = __fdiv_rn(ts, a.den_sup);
+            const float l_dis = __fdiv_rn(td, a.den_dis);
+            a.loss[0] = __fadd_rn(__fadd_rn(l_sup, 0.f), l_dis);
+        }
+    }
+}
+
+struct Loss2Args {
+    const float *z, *zg, *y, *distill;
+    float *loss, *dz;
+    float* ws;
+    int64_t n;
+    int variant;
+};
+
+__global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_constant__ Loss2Args a) {
+    __shared__ float s_red[32];
+    __shared__ int s_redi[32];
+    __shared__ float s_den;
+    cg::grid_group grid = cg::this_grid();
+    int* wsi = reinterpret_cast<int*>(a.ws);
+    const int64_t stride = (int64_t)gridDim.x * kLossThreads * kLossUnroll;
+    const int64_t first = (int64_t)blockIdx.x * kLossThreads * kLossUnroll + threadIdx.x;
+
+    // ---- phase 1: denominator.  sup/distill are 0/1 masks, so the sums are exact integers ----
+    int n_dis = 0, n_all = 0;
+    for (int64_t base = first; base < a.n; base += stride) {
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int64_t e = base + (int64_t)u * kLossThreads;
+            if (e < a.n) { n_dis += (a.distill[e] != 0.f) ? 1 : 0; n_all += 1; }
+        }
+    }
+    const int b_dis = block_sum_i(n_dis, s_redi);
+    const int b_all = block_sum_i(n_all, s_redi);
+    if (threadIdx.x == 0) { wsi[2 * kLossMaxGrid + blockIdx.x] = b_dis; wsi[3 * kLossMaxGrid + blockIdx.x] = b_all; }
+    grid.sync();
+    {
+        int td = 0, ta = 0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kLossThreads) { td += wsi[2 * kLossMaxGrid + b]; ta += wsi[3 * kLossMaxGrid + b]; }
+        td = block_sum_i(td, s_redi);
+        ta = block_sum_i(ta, s_redi);
+        if (threadIdx.x == 0) {
+            const float sum_dis = (float)td, sum_sup = (float)(ta - td);
+            // :1188  sup_cls.sum()          :1187  sup_cls.sum() + distill_cls.sum()
+            s_den = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+        }
+        __syncthreads();
+    }
+    const float den = s_den;
+    const float g = __fdiv_rn(1.f, den);  // d loss / d numerator
+
+    // ---- phase 2: numerators + gradient -----------------------------------------------------
+    float num_sup = 0.f, num_dis = 0.f;
+    for (int64_t base = first; base < a.n; base += stride) {
+        float vz[kLossUnroll], vg[kLossUnroll], vy[kLossUnroll], vd[kLossUnroll];
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int64_t e = base + (int64_t)u * kLossThreads;
+            const bool ok = e < a.n;
+            vz[u] = ok ? a.z[e] : 0.f;
+            vy[u] = ok ? a.y[e] : 0.f;
+            vd[u] = ok ? a.distill[e] : 0.f;
+            vg[u] = (ok && a.variant == FMLP_LOSS2_SUP_DIS) ? a.zg[e] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kLossUnroll; ++u) {
+            const int64_t e = base + (int64_t)u * kLossThreads;
+            if (e >= a.n) continue;
+            const float p = sigmoid_ref(vz[u]);
+            const float dist = vd[u];
+            const float sup = (dist != 0.f) ? 0.f : 1.f;  // (~distill_cls.bool()).float()  (:1173)
+            // loss_sup * sup_cls, backward: (g * sup) into BCE backward
+            num_sup += __fmul_rn(bce_fwd(p, vy[u]), sup);
+            float gp = bce_bwd(__fmul_rn(g, sup), p, vy[u]);
+            if (a.variant == FMLP_LOSS2_SUP_DIS) {
+                const float pg = sigmoid_ref(vg[u]);
+                const float d = __fsub_rn(p, pg);
+                num_dis += __fmul_rn(__fmul_rn(d, d), dist);
+                gp = __fadd_rn(gp, mse_bwd(__fmul_rn(g, dist), p, pg));
+            }
+            a.dz[e] = sigmoid_bwd(gp, p);
+        }
+    }
+    const float bn_sup = block_sum(num_sup, s_red);
+    const float bn_dis = block_sum(num_dis, s_red);
+    if (threadIdx.x == 0) { a.ws[blockIdx.x] = bn_sup; a.ws[kLossMaxGrid + blockIdx.x] = bn_dis; }
+    grid.sync();
+    if (blockIdx.x == 0) {
+        float ts = 0.f, td = 0.f;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kLossThreads) { ts += a.ws[b]; td += a.ws[kLossMaxGrid + b]; }
+        ts = block_sum(ts, s_red);
+        td = block_sum(td, s_red);
+        if (threadIdx.x == 0) {
+            const float num = a.variant == FMLP_LOSS2_SUP ? ts : __fadd_rn(ts, td);
+            a.loss[0] = __fdiv_rn(num, den);
+        }
+    }
+}
+
+__global__ void scale_kernel(float* x, int64_t n, const float* scale) {
+    const float s = *scale;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = __fmul_rn(x[i], s);
+}
+
+template <typename Kern>
+static int coop_grid(Kern kern, int64_t n, int* grid_out) {
+    static int blocks_per_sm = 0;  // per kernel instantiation
+    if (blocks_per_sm == 0) {
+        int b = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kLossThreads, 0);
+        if (e != cudaSuccess) return (int)e;
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    int64_t want = (n + (int64_t)kLossThreads * kLossUnroll - 1) / ((int64_t)kLossThreads * kLossUnroll);
+    int64_t cap = (int64_t)sms * blocks_per_sm;
+    if (cap > kLossMaxGrid) cap = kLossMaxGrid;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    *grid_out = (int)want;
+    return FMLP_OK;
+}
+
+}  // namespace fmlp
+
+using namespace fmlp;
+
+extern "C" size_t fmlp_loss_ws_bytes(int64_t B, int C) {
+    (void)B; (void)C;
+    return (size_t)4 * kLossMaxGrid * sizeof(float);
+}
+
+extern "C" int fmlp_loss_stage1_f32(const float* z1, const float* z2, const float* z3, const float* z4,
+                                    const float* y, int64_t B, int C, uint32_t active, uint32_t missing,
+                                    int bs, float* loss, float* dz1, float* dz2, void* ws,
+                                    size_t ws_bytes, fmlp_stream_t stream) {
+    if (!z1 || !z2 || !z3 || !z4 || !y || !loss || !dz1 || !dz2 || !ws || B < 0 || C < 1 ||
+        C > FMLP_MAX_CLASSES || bs < 1)
+        return FMLP_ERR_BAD_ARG;
+    if (ws_bytes < fmlp_loss_ws_bytes(B, C)) return FMLP_ERR_WORKSPACE;
+    const uint32_t cmask = C < 32 ? ((1u << C) - 1u) : 0xffffffffu;
+    Loss1Args a;
+    a.z1 = z1; a.z2 = z2; a.z3 = z3; a.z4 = z4; a.y = y; a.loss = loss; a.dz1 = dz1; a.dz2 = dz2;
+    a.ws = (float*)ws; a.n = B * C; a.C = C; a.active = active & cmask; a.missing = missing & cmask & ~active;
+    // self.args.batch_size * self.args.annotation_num / * len(negetive_class_list_client) (:956-959)
+    a.den_sup = (float)((int64_t)bs * __builtin_popcount(a.active));
+    a.den_dis = (float)((int64_t)bs * __builtin_popcount(a.missing));
+    int grid = 1;
+    int rc = coop_grid(loss_stage1_kernel, a.n, &grid);
+    if (rc != FMLP_OK) return rc;
+    void* args[] = {(void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)loss_stage1_kernel, dim3(grid), dim3(kLossThreads),
+                                                args, 0, (cudaStream_t)stream);
+    return e == cudaSuccess ? launch_status() : (int)e;
+}
+
+extern "C" int fmlp_loss_stage2_f32(const float* z, const float* zg, const float* y, const float* distill,
+                                    int64_t B, int C, int variant, float* loss, float* dz, void* ws,
+                                    size_t ws_bytes, fmlp_stream_t stream) {
+    if (!z || !y || !distill || !loss || !dz || !ws || B < 0 || C < 1 || C > FMLP_MAX_CLASSES)
+        return FMLP_ERR_BAD_ARG;
+    if (variant != FMLP_LOSS2_SUP && variant != FMLP_LOSS2_SUP_DIS) return FMLP_ERR_BAD_ARG;
+    if (variant == FMLP_LOSS2_SUP_DIS && !zg) return FMLP_ERR_BAD_ARG;
+    if (ws_bytes < fmlp_loss_ws_bytes(B, C)) return FMLP_ERR_WORKSPACE;
+    Loss2Args a;
+    a.z = z; a.zg = zg; a.y = y; a.distill = distill; a.loss = loss; a.dz = dz; a.ws = (float*)ws;
+    a.n = B * C; a.variant = variant;
+    int grid = 1;
+    int rc = coop_grid(loss_stage2_kernel, a.n, &grid);
+    if (rc != FMLP_OK) return rc;
+    void* args[] = {(void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)loss_stage2_kernel, dim3(grid), dim3(kLossThreads),
+                                                args, 0, (cudaStream_t)stream);
+    return e == cudaSuccess ? launch_status() : (int)e;
+}
+
+extern "C" int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream) {
+    if (!x || !scale_dev || n < 0) return FMLP_ERR_BAD_ARG;
+    if (n == 0) return FMLP_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int sms = sm_count();
+    if (sms > 0 && blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale_dev);
+    return launch_status();
+}

@@ -1,0 +1,285 @@
+// tag_select.cu — K3b: sign split + top-fraction selection, K3c: label / mask fill.
+//
+// Replaces utils/local_training.py:1061-1112 (np.where sign split, int(frac*len) counts,
+// utils/utils.py:24-35 max_m_indices / min_n_indices = Python `sorted(enumerate(list))`) and
+// DatasetSplit_pseudo.__getitem__ (:1456-1477).  The reference sorts all N similarities in the
+// interpreter twice per class; here one CTA per (segment, class) radix-SELECTS the m-th largest
+// clean and k-th smallest noise value (both are "largest |sim|" on their side), so only
+// histogram passes over an L2-resident [N] vector are needed.
+//
+// Ordering key: comp = (bits(|sim|) << 32) | (0xFFFFFFFF - local_row).  Larger comp = picked
+// first; equal similarities are therefore taken in increasing row order, which is exactly the
+// tie behaviour of Python's stable sort in both max_m_indices (reverse=True keeps the original
+// order of equal elements) and min_n_indices.  All comps of an item are distinct, so the
+// selection "comp >= T" has exactly m (resp. k) members.
+#include "common.cuh"
+
+namespace fmlp {
+
+constexpr int kSelThreads = 512;
+constexpr int kSelBins = 2048;  // 11-bit digits; 4 bins per thread in the scan
+
+struct SelArgs {
+    const float* sim;
+    uint8_t* tag;
+    int32_t* counts;     // [S][C][4]
+    int32_t* sel;        // [S][C][2][cap]
+    unsigned long long* cand;  // ws [S][C][2][cap]
+    int64_t ld_sim, ld_tag, cap;
+    double clean_frac, noise_frac;
+    int C;
+    SegTable seg;  // mask_a = missing classes
+};
+
+// Block-wide exclusive scan of one int per thread (kSelThreads threads); returns the exclusive
+// prefix and writes the grand total to *total (same value in every thread).
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp /*[kSelThreads/32 + 1]*/, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // s_warp reuse
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < kSelThreads / 32) ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < kSelThreads / 32) s_warp[lane] = winc - w;  // exclusive warp offsets
+        if (lane == kSelThreads / 32 - 1) s_warp[kSelThreads / 32] = winc;
+    }
+    __syncthreads();
+    *total = s_warp[kSelThreads / 32];
+    return s_warp[warp] + inc - v;
+}
+
+__device__ __forceinline__ unsigned long long make_comp(float s, uint32_t local_row) {
+    const uint32_t mag = __float_as_uint(fabsf(s));  // -0.0 -> 0, NaN never reaches here
+    return ((unsigned long long)mag << 32) | (unsigned long long)(0xFFFFFFFFu - local_row);
+}
+// side: 0 clean (sim >= 0), 1 noise (sim < 0), -1 neither (NaN) — np.where(sim >= 0) / (sim < 0)
+__device__ __forceinline__ int side_of(float s) { return s >= 0.f ? 0 : (s < 0.f ? 1 : -1); }
+
+__global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid_constant__ SelArgs a) {
+    __shared__ int s_hist[2][kSelBins];  // reused as the rank staging tile (2048 x u64)
+    __shared__ int s_warp[kSelThreads / 32 + 1];
+    __shared__ int s_found[3];           // bin, remaining-in-bin, bin count
+    __shared__ int s_count[2];
+
+    const int item = blockIdx.x;
+    const int s = item / a.C, c = item - s * a.C;
+    int32_t* counts = a.counts + (int64_t)item * 4;
+    if (!((a.seg.mask_a[s] >> c) & 1u)) {
+        if (threadIdx.x < 4) counts[threadIdx.x] = 0;
+        return;
+    }
+    const int64_t r0 = a.seg.rows[s];
+    const uint32_t n = (uint32_t)(a.seg.rows[s + 1] - r0);
+    const float* sim = a.sim + (int64_t)c * a.ld_sim + r0;
+    uint8_t* tag = a.tag + (int64_t)c * a.ld_tag + r0;
+
+    unsigned long long prefix[2] = {0ull, 0ull};
+    unsigned long long thresh[2] = {~0ull, ~0ull};  // comp >= thresh selects; ~0 selects nothing
+    int rem[2] = {0, 0};
+    bool done[2] = {false, false};
+    int n_side[2] = {0, 0}, want[2] = {0, 0};
+
+    // digits of the 63 significant comp bits, most significant first: 5 x 11 bits + 8 bits
+    for (int pass = 0; pass < 6; ++pass) {
+        if (done[0] && done[1]) break;
+        const int shift = pass < 5 ? 52 - 11 * pass : 0;
+        const int width = pass < 5 ? 11 : 8;
+        for (int i = threadIdx.x; i < 2 * kSelBins; i += kSelThreads) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+        const unsigned long long dmask = (1ull << width) - 1ull;
+        for (uint32_t i = threadIdx.x; i < n; i += kSelThreads) {
+            if (tag[i] != 0) continue;
+            const float v = sim[i];
+            const int sd = side_of(v);
+            if (sd < 0 || done[sd]) continue;
+            const unsigned long long comp = make_comp(v, i);
+            if (pass == 0 || (comp >> (shift + width)) == prefix[sd])
+                atomicAdd(&s_hist[sd][(int)((comp >> shift) & dmask)], 1);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (done[sd]) continue;  // uniform across the CTA
+            // bins are visited from the top: thread t owns bins 2047-4t .. 2047-4t-3
+            int h[4];
+            int ls = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { h[j] = s_hist[sd][kSelBins - 1 - (4 * (int)threadIdx.x + j)]; ls += h[j]; }
+            int total;
+            const int ex = block_exclusive_scan(ls, s_warp, &total);
+            if (pass == 0) {
+                n_side[sd] = total;
+                const double frac = sd == 0 ? a.clean_frac : a.noise_frac;
+                long long w = (long long)__dmul_rn(frac, (double)total);  // int(frac * len), :1069-1070
+                if (w < 0) w = 0;
+                if (w > total) w = total;
+                want[sd] = (int)w;
+                rem[sd] = (int)w;
+                if (w == 0) { done[sd] = true; continue; }
+            }
+            if (ex < rem[sd] && rem[sd] <= ex + ls) {
+                int cum = ex;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cum < rem[sd] && rem[sd] <= cum + h[j]) {
+                        s_found[0] = kSelBins - 1 - (4 * (int)threadIdx.x + j);
+                        s_found[1] = rem[sd] - cum;
+                        s_found[2] = h[j];
+                    }
+                    cum += h[j];
+                }
+            }
+            __syncthreads();
+            const int bin = s_found[0], rem_in = s_found[1], bin_count = s_found[2];
+            __syncthreads();
+            prefix[sd] = (prefix[sd] << width) | (unsigned long long)bin;
+            if (bin_count == rem_in) {  // whole bin is taken: threshold = smallest comp with this prefix
+                thresh[sd] = prefix[sd] << shift;
+                done[sd] = true;
+            } else {
+                rem[sd] = rem_in;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- compaction: mark the tag state and collect the selected comps -------------------
+    if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kSelThreads) {
+        if (tag[i] != 0) continue;
+        const float v = sim[i];
+        const int sd = side_of(v);
+        if (sd < 0) continue;
+        const unsigned long long comp = make_comp(v, i);
+        if (comp >= thresh[sd]) {
+            const int slot = atomicAdd(&s_count[sd], 1);
+            if (slot < a.cap) a.cand[((int64_t)item * 2 + sd) * a.cap + slot] = comp;
+            tag[i] = (uint8_t)(1 + sd);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counts[0] = n_side[0]; counts[1] = n_side[1]; counts[2] = want[0]; counts[3] = want[1];
+    }
+
+    // ---- rank order: position = number of selected comps that are larger -----------------
+    unsigned long long* tile = reinterpret_cast<unsigned long long*>(&s_hist[0][0]);  // 2048 entries
+    constexpr int kTile = 2048;
+    for (int sd = 0; sd < 2; ++sd) {
+        const int cnt = min((int64_t)s_count[sd], a.cap);
+        const unsigned long long* cand = a.cand + ((int64_t)item * 2 + sd) * a.cap;
+        int32_t* out = a.sel + ((int64_t)item * 2 + sd) * a.cap;
+        for (int e0 = 0; e0 < cnt; e0 += kSelThreads) {
+            const int e = e0 + threadIdx.x;
+            const unsigned long long mine = e < cnt ? cand[e] : 0ull;
+            int rank = 0;
+            for (int t0 = 0; t0 < cnt; t0 += kTile) {
+                __syncthreads();
+                for (int j = threadIdx.x; j < kTile && t0 + j < cnt; j += kSelThreads) tile[j] = cand[t0 + j];
+                __syncthreads();
+                const int lim = min(kTile, cnt - t0);
+                for (int j = 0; j < lim; ++j) rank += (tile[j] > mine) ? 1 : 0;
+            }
+            if (e < cnt)
+                out[rank] = (int32_t)(r0 + (int64_t)(0xFFFFFFFFu - (uint32_t)(mine & 0xFFFFFFFFull)));
+        }
+        __syncthreads();
+    }
+}
+
+struct FillArgs {
+    const float* labels_in;
+    const uint8_t* tag;
+    float* y;
+    float* distill;
+    float* sup;
+    int64_t ld_tag;
+    int C;
+    SegTable seg;  // mask_a = active, mask_b = missing
+};
+
+__global__ void __launch_bounds__(256) mask_fill_kernel(const __grid_constant__ FillArgs a) {
+    const int64_t n_el = a.seg.rows[a.seg.S] * a.C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / a.C;
+        const int c = (int)(e - row * a.C);
+        const int s = find_segment(a.seg.rows, a.seg.S, row);
+        float y = 0.f, dis = 0.f;
+        if ((a.seg.mask_a[s] >> c) & 1u) {
+            y = a.labels_in[e];                       // annotated class keeps its label (:1458-1460)
+        } else if ((a.seg.mask_b[s] >> c) & 1u) {
+            const uint8_t t = a.tag[(int64_t)c * a.ld_tag + row];
+            y = (t == 2) ? 1.f : 0.f;                 // in the noise list -> pseudo-positive (:1464-1466)
+            dis = (t == 0) ? 1.f : 0.f;               // in neither list -> distilled (:1467-1468)
+        }
+        if (a.y) a.y[e] = y;
+        if (a.distill) a.distill[e] = dis;
+        if (a.sup) a.sup[e] = 1.f - dis;              // sup_cls = ~distill_cls (:1173)
+    }
+}
+
+}  // namespace fmlp
+
+using namespace fmlp;
+
+extern "C" size_t fmlp_tag_select_ws_bytes(int S, int C, int64_t cap) {
+    if (S < 1 || C < 1 || cap < 0) return 0;
+    const size_t n = (size_t)S * C * 2 * (size_t)(cap > 0 ? cap : 1);
+    return n * sizeof(unsigned long long);
+}
+
+extern "C" int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, int64_t ld_tag, int C,
+                               int S, const int64_t* seg_rows, const uint32_t* seg_missing,
+                               double clean_frac, double noise_frac, int32_t* counts, int32_t* sel,
+                               int64_t cap, void* ws, size_t ws_bytes, fmlp_stream_t stream) {
+    if (!sim || !tag || !seg_missing || !counts || !sel || !ws || C < 1 || C > FMLP_MAX_CLASSES || cap < 1)
+        return FMLP_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(ws) & 7u) return FMLP_ERR_UNSUPPORTED;
+    if (ws_bytes < fmlp_tag_select_ws_bytes(S, C, cap)) return FMLP_ERR_WORKSPACE;
+    SelArgs a;
+    int rc = fill_seg_table(a.seg, S, seg_rows, seg_missing, nullptr);
+    if (rc != FMLP_OK) return rc;
+    for (int s = 0; s < S; ++s)
+        if (seg_rows[s + 1] - seg_rows[s] > 0x7fffffffLL) return FMLP_ERR_UNSUPPORTED;
+    if (ld_sim < seg_rows[S] || ld_tag < seg_rows[S]) return FMLP_ERR_BAD_ARG;
+    a.sim = sim; a.tag = tag; a.counts = counts; a.sel = sel; a.cand = (unsigned long long*)ws;
+    a.ld_sim = ld_sim; a.ld_tag = ld_tag; a.cap = cap; a.clean_frac = clean_frac; a.noise_frac = noise_frac;
+    a.C = C;
+    tag_select_kernel<<<(unsigned)(S * C), kSelThreads, 0, (cudaStream_t)stream>>>(a);
+    return launch_status();
+}
+
+extern "C" int fmlp_mask_fill(const float* labels_in, const uint8_t* tag, int64_t ld_tag, int C, int S,
+                              const int64_t* seg_rows, const uint32_t* seg_active,
+                              const uint32_t* seg_missing, float* y, float* distill, float* sup,
+                              fmlp_stream_t stream) {
+    if (!labels_in || !tag || !seg_active || !seg_missing || C < 1 || C > FMLP_MAX_CLASSES)
+        return FMLP_ERR_BAD_ARG;
+    FillArgs a;
+    int rc = fill_seg_table(a.seg, S, seg_rows, seg_active, seg_missing);
+    if (rc != FMLP_OK) return rc;
+    if (ld_tag < seg_rows[S]) return FMLP_ERR_BAD_ARG;
+    const int64_t n_el = seg_rows[S] * C;
+    if (n_el == 0) return FMLP_OK;
+    a.labels_in = labels_in; a.tag = tag; a.y = y; a.distill = distill; a.sup = sup; a.ld_tag = ld_tag; a.C = C;
+    const int sms = sm_count();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    int64_t blocks = (n_el + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    mask_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status();
+}

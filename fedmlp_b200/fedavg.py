@@ -1,0 +1,292 @@
+"""Server aggregation — drop-in for the reference's utils/FedAvg.py.
+
+Same call surface: `FedAvg(w, dict_len)`, `Fed_w(w, weight)`, `FedAvg_proto(Prototypes, weight,
+class_active_client_list)`, `FedAvg_tao(t, weight, class_active_client_list=None)`
+(reference: utils/FedAvg.py:7-14, :16-23, :72-93, :51-70; call sites main.py:218-234).
+
+`FedAvg` returns an OrderedDict with the reference's keys, order and result dtypes (fp32 stays
+fp32, int64 BatchNorm counters become float32 — the true-division quirk) on the
+device of the inputs.  The arithmetic runs in libfedmlp_b200 (fedavg.cu): one launch over the
+flat parameter buffers when the clients are `FlatStateDict`s (or views laid out like one), else
+one multi-tensor launch that reads the K x T scattered tensors in place.
+"""
+from __future__ import annotations
+
+import numbers
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from .flat import FlatLayout, FlatStateDict, flat_view_of, layout_of
+
+_plan_cache: dict = {}
+
+
+def _is_integral(x) -> bool:
+    return isinstance(x, (numbers.Integral, np.integer)) and not isinstance(x, bool)
+
+
+def _multi_plan(layout: FlatLayout, device):
+    """Device-resident chunk tables of the multi-tensor kernel for one layout (cached)."""
+    key = (layout, str(device))
+    plan = _plan_cache.get(key)
+    if plan is not None:
+        return plan
+    f_idx, i_idx = layout.float_index, layout.int_index
+    chunk_tensor, chunk_start = [], []
+    for t, i in enumerate(f_idx):
+        n = layout.numels[i]
+        for s in range(0, n, cabi.FEDAVG_CHUNK):
+            chunk_tensor.append(t)
+            chunk_start.append(s)
+    elem_tensor, elem_index = [], []
+    for t, i in enumerate(i_idx):
+        for e in range(layout.numels[i]):
+            elem_tensor.append(t)
+            elem_index.append(e)
+    plan = dict(
+        f_idx=f_idx, i_idx=i_idx,
+        numel=torch.tensor([layout.numels[i] for i in f_idx], dtype=torch.int64, device=device),
+        chunk_tensor=torch.tensor(chunk_tensor, dtype=torch.int32, device=device),
+        chunk_start=torch.tensor(chunk_start, dtype=torch.int64, device=device),
+        n_chunks=len(chunk_tensor),
+        elem_tensor=torch.tensor(elem_tensor, dtype=torch.int32, device=device),
+        elem_index=torch.tensor(elem_index, dtype=torch.int64, device=device),
+        n_elems=len(elem_tensor),
+        f_off=np.array([layout.offsets[i] for i in f_idx], dtype=np.int64),
+        i_off=np.array([layout.offsets[i] for i in i_idx], dtype=np.int64),
+    )
+    _plan_cache[key] = plan
+    return plan
+
+
+def _check_same_keys(w):
+    keys = list(w[0].keys())
+    for i in range(1, len(w)):
+        if list(w[i].keys()) != keys:
+            raise KeyError(f"FedAvg: client {i} has different state_dict keys than client 0")
+
+
+def fedavg_flat_buffers(bufs, weights, out=None, divisor=None, divide=True):
+    """K-way weighted fold of K flat fp32 CUDA buffers of equal length (the bench / sweep entry
+    point; also what FedAvg uses underneath).  Any K: folds in groups of MAX_CLIENTS, in order."""
+    K = len(bufs)
+    if K == 0:
+        raise ValueError("FedAvg of zero clients")
+    cabi.require_cuda(*bufs)
+    P = bufs[0].numel()
+    dev = bufs[0].device
+    if out is None:
+        out = torch.empty(P, dtype=torch.float32, device=dev)
+    if divisor is None:
+        divisor = sum(weights)
+    lib = cabi.lib()
+    with torch.cuda.device(dev):
+        st = cabi.stream_ptr(dev)
+        for g0 in range(0, K, cabi.MAX_CLIENTS):
+            g1 = min(K, g0 + cabi.MAX_CLIENTS)
+            flags = 0
+            if g0 > 0:
+                flags |= cabi.FEDAVG_ACCUMULATE
+            if g1 == K and divide:
+                flags |= cabi.FEDAVG_DIVIDE
+            srcs = cabi.ptr_array([b.data_ptr() for b in bufs[g0:g1]])
+            ws = cabi.f32_array(weights[g0:g1])
+            cabi.check(lib.fmlp_fedavg_flat_f32(srcs, ws, g1 - g0, P, float(divisor), flags,
+                                                out.data_ptr(), st), "fmlp_fedavg_flat_f32")
+    return out
+
+
+def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev):
+    lib = cabi.lib()
+    K = len(ptrs)
+    if K > cabi.MAX_CLIENTS and integral:
+        raise NotImplementedError("int64 FedAvg with integer weights supports at most 64 clients per call")
+    st = cabi.stream_ptr(dev)
+    for g0 in range(0, K, cabi.MAX_CLIENTS):
+        g1 = min(K, g0 + cabi.MAX_CLIENTS)
+        flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (cabi.FEDAVG_DIVIDE if g1 == K else 0)
+        cabi.check(lib.fmlp_fedavg_flat_i64(cabi.ptr_array(ptrs[g0:g1]), cabi.f64_array(weights[g0:g1]), g1 - g0, J,
+                                            float(divisor), 1 if integral else 0, flags, out_ptr, st),
+                   "fmlp_fedavg_flat_i64")
+
+
+def _fedavg_cuda(w, dict_len):
+    layout = layout_of(w[0])
+    dev = next(iter(w[0].values())).device
+    K = len(w)
+    integral = all(_is_integral(x) for x in dict_len)
+    divisor = sum(dict_len)
+    out = FlatStateDict.empty(layout, dev, ints_as_float=True)
+    lib = cabi.lib()
+    with torch.cuda.device(dev):
+        st = cabi.stream_ptr(dev)
+        views = [flat_view_of(sd) if layout_of(sd) is layout else None for sd in w]
+        if all(v is not None for v in views):
+            # ---- flat path: K pointers, one streaming launch ---------------------------
+            if layout.n_f32:
+                bufs = [v[0] for v in views]
+                for g0 in range(0, K, cabi.MAX_CLIENTS):
+                    g1 = min(K, g0 + cabi.MAX_CLIENTS)
+                    flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (cabi.FEDAVG_DIVIDE if g1 == K else 0)
+                    cabi.check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array(bufs[g0:g1]), cabi.f32_array(dict_len[g0:g1]),
+                                                        g1 - g0, layout.n_f32, float(divisor), flags,
+                                                        out.flat_f32.data_ptr(), st), "fmlp_fedavg_flat_f32")
+            if layout.n_i64:
+                _fedavg_i64_flat([v[1] for v in views], list(dict_len), layout.n_i64, divisor, integral,
+                                 out.flat_f32.data_ptr() + 4 * layout.n_f32, dev)
+            return out
+        # ---- multi-tensor path: read the scattered tensors in place ---------------------
+        plan = _multi_plan(layout, dev)
+        if K > cabi.MAX_CLIENTS:
+            raise NotImplementedError(
+                "FedAvg over more than 64 scattered state_dicts: wrap the clients with "
+                "FlatStateDict.from_state_dict (flat path has no client limit)")
+        f_idx, i_idx = plan["f_idx"], plan["i_idx"]
+        Tf, Ti = len(f_idx), len(i_idx)
+        vals = [list(sd.values()) for sd in w]
+        for sd_vals in vals:
+            for v in sd_vals:
+                if not v.is_contiguous():
+                    raise ValueError("FedAvg: non-contiguous state_dict tensor")
+        table = np.empty(Tf * K + Tf + Ti * K + Ti, dtype=np.int64)
+        if Tf:
+            src = np.array([[vals[i][t].data_ptr() for i in range(K)] for t in f_idx], dtype=np.int64)
+            table[:Tf * K] = src.reshape(-1)
+            table[Tf * K:Tf * K + Tf] = out.flat_f32.data_ptr() + 4 * plan["f_off"]
+        o = Tf * K + Tf
+        if Ti:
+            src = np.array([[vals[i][t].data_ptr() for i in range(K)] for t in i_idx], dtype=np.int64)
+            table[o:o + Ti * K] = src.reshape(-1)
+            table[o + Ti * K:] = out.flat_f32.data_ptr() + 4 * (layout.n_f32 + plan["i_off"])
+        table_dev = torch.from_numpy(table).to(dev, non_blocking=False)
+        base = table_dev.data_ptr()
+        if Tf:
+            cabi.check(lib.fmlp_fedavg_multi_f32(base, base + 8 * Tf * K, plan["numel"].data_ptr(),
+                                                 plan["chunk_tensor"].data_ptr(), plan["chunk_start"].data_ptr(),
+                                                 plan["n_chunks"], Tf, cabi.f32_array(dict_len), K, float(divisor),
+                                                 cabi.FEDAVG_DIVIDE, st), "fmlp_fedavg_multi_f32")
+        if Ti:
+            cabi.check(lib.fmlp_fedavg_multi_i64(base + 8 * o, base + 8 * (o + Ti * K), plan["elem_tensor"].data_ptr(),
+                                                 plan["elem_index"].data_ptr(), plan["n_elems"], Ti,
+                                                 cabi.f64_array(dict_len), K, float(divisor), 1 if integral else 0,
+                                                 cabi.FEDAVG_DIVIDE, st), "fmlp_fedavg_multi_i64")
+        out._keepalive = table_dev  # the launch is asynchronous; keep the table until the dict dies
+    return out
+
+
+def _stage_cpu_client(sd, dev):
+    """Pack a CPU state_dict into pinned flat buffers (one foreach copy) and upload them."""
+    lay = layout_of(sd)
+    pin_f = torch.zeros(max(lay.n_f32, 1), dtype=torch.float32, pin_memory=True)
+    pin_i = torch.zeros(max(lay.n_i64, 1), dtype=torch.int64, pin_memory=True)
+    views = []
+    for i in range(len(lay.keys)):
+        n, off = lay.numels[i], lay.offsets[i]
+        buf = pin_i if lay.is_int[i] else pin_f
+        views.append(buf[off:off + n].view(lay.shapes[i]))
+    torch._foreach_copy_(views, [v.detach() for v in sd.values()])
+    d = FlatStateDict.empty(lay, dev)
+    if lay.n_f32:
+        d.flat_f32.copy_(pin_f[:lay.n_f32], non_blocking=True)
+    if d.flat_i64 is not None:
+        d.flat_i64.copy_(pin_i[:lay.n_i64], non_blocking=True)
+    d._keepalive = (pin_f, pin_i)
+    return d
+
+
+def FedAvg(w, dict_len):
+    """Weighted average of K client state_dicts (reference utils/FedAvg.py:7-14).
+
+    w: list of K OrderedDict[str, Tensor] with identical keys; dict_len: K ints or floats.
+    CUDA inputs are reduced in place on their device.  CPU inputs (the reference's stage 2 hands
+    over `net.cpu()` weights, local_training.py:1251) are staged through pinned memory, reduced
+    on the current CUDA device and returned as CPU tensors."""
+    if len(w) == 0:
+        raise ValueError("FedAvg of zero clients")
+    if len(w) != len(dict_len):
+        raise ValueError("FedAvg: len(w) != len(dict_len)")
+    _check_same_keys(w)
+    first = next(iter(w[0].values()))
+    if first.is_cuda:
+        for sd in w:
+            cabi.require_cuda(*sd.values())
+        return _fedavg_cuda(w, dict_len)
+    if not torch.cuda.is_available():
+        raise cabi.FedMLPNativeError("FedAvg needs a CUDA device (fedmlp_b200 has no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    staged = [_stage_cpu_client(sd, dev) for sd in w]
+    res = _fedavg_cuda(staged, dict_len)
+    host_flat = res.flat_f32.cpu()
+    out = OrderedDict()
+    lay = res.layout
+    for i, k in enumerate(lay.keys):
+        n = lay.numels[i]
+        off = lay.offsets[i] if not lay.is_int[i] else lay.n_f32 + lay.offsets[i]
+        out[k] = host_flat[off:off + n].view(lay.shapes[i])
+    return out
+
+
+def Fed_w(w, weight):
+    """utils/FedAvg.py:16-23 — same body as FedAvg."""
+    return FedAvg(w, weight)
+
+
+def FedAvg_proto(Prototypes, weight, class_active_client_list):
+    """Per-class weighted mean of the clients' prototypes (reference utils/FedAvg.py:72-93).
+    Prototypes: list of K [2C, D] tensors; returns [2C, D] on the device of the inputs
+    (the reference works on CPU tensors and returns a CPU tensor)."""
+    K = len(Prototypes)
+    if K == 0:
+        raise ValueError("FedAvg_proto of zero clients")
+    if K > cabi.MAX_CLIENTS:
+        raise NotImplementedError("FedAvg_proto supports at most 64 clients per call")
+    p0 = Prototypes[0]
+    was_cpu = not p0.is_cuda
+    if was_cpu and not torch.cuda.is_available():
+        raise cabi.FedMLPNativeError("FedAvg_proto needs a CUDA device (no CPU fallback)")
+    dev = p0.device if p0.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    stacked = torch.stack([p.to(dev, dtype=torch.float32) for p in Prototypes]).contiguous()
+    C2, D = stacked.shape[1], stacked.shape[2]
+    C = C2 // 2
+    if len(class_active_client_list) > C:
+        raise ValueError("class_active_client_list longer than the number of classes")
+    masks = [0] * C
+    for cls, clients in enumerate(class_active_client_list):
+        for cid in clients:
+            if not 0 <= int(cid) < K:
+                raise IndexError(f"client id {cid} out of range")
+            masks[cls] |= 1 << int(cid)
+    out = torch.zeros(C2, D, dtype=torch.float32, device=dev)
+    # the reference only fills the rows of the classes it iterates over; the others stay 0
+    n_listed = len(class_active_client_list)
+    with torch.cuda.device(dev):
+        tmp = torch.empty(C2, D, dtype=torch.float32, device=dev)
+        cabi.check(cabi.lib().fmlp_proto_avg_f32(stacked.data_ptr(), K, C, D, cabi.f64_array(weight),
+                                                 cabi.u64_array(masks), tmp.data_ptr(), cabi.stream_ptr(dev)),
+                   "fmlp_proto_avg_f32")
+        out[:2 * n_listed] = tmp[:2 * n_listed]
+    return out.cpu() if was_cpu else out
+
+
+def FedAvg_tao(t, weight, class_active_client_list=None):
+    """Per-class weighted mean of the clients' difficulty statistics t (reference
+    utils/FedAvg.py:51-70).  K x C float64 scalars on the host, exactly like the reference:
+    this is host-side bookkeeping (the values are only printed by the tagger,
+    local_training.py:1068), not a device kernel."""
+    n = len(t[0])
+    avg = np.zeros(n, dtype=np.float64)
+    if class_active_client_list is None:
+        for i, tao in enumerate(t):
+            avg += np.asarray(tao, dtype=np.float64) * float(weight[i])
+        return avg / float(sum(weight))
+    for cls, clients in enumerate(class_active_client_list):
+        wsum = 0.0
+        for i, tao in enumerate(t):
+            if i in clients:
+                avg[cls] += tao[cls] * float(weight[i])
+                wsum += float(weight[i])
+        avg[cls] = 1.0 if len(clients) == 0 else avg[cls] / wsum
+    return avg

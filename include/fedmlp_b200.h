@@ -1,0 +1,213 @@
+/*
+ * fedmlp_b200.h — C ABI of libfedmlp_b200.so
+ *
+ * Drop-in boundary for the FedMLP per-round hot path (tag + prototypes + loss + FedAvg) on
+ * NVIDIA B200 (sm_100a).  The reference (szbonaldo/FedMLP) is pure Python/PyTorch and has no
+ * FFI of its own; every entry point below therefore cites the reference
+ * *Python* block it replaces.  Host code (fedmlp_b200/*.py, ctypes) keeps the reference's call
+ * surface and forwards raw device pointers + the caller's CUDA stream to these functions.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, a NEGATIVE fmlp_status for argument errors, or a POSITIVE
+ *     cudaError_t value if a CUDA runtime call / launch failed.  No C++ exception crosses.
+ *   - no allocation, no host synchronisation, no hidden streams: every kernel is launched on
+ *     `stream` on the caller's current device; workspaces are caller-provided
+ *     (query the size with the matching *_ws_bytes function).
+ *   - pointers named *_dev / unqualified tensors are DEVICE pointers (borrowed);
+ *     pointers documented "host" are small host arrays that are copied into the kernel's
+ *     parameter block at launch time (so a launch is self-contained and graph-capturable).
+ *   - matrices are row-major and dense unless a leading dimension is given.
+ *   - "segment" = one simulated federated client whose rows are stored contiguously in a
+ *     batched [N_total, D] matrix; `seg_rows` is the host prefix array [S+1] of row offsets.
+ *     A single client is S = 1, seg_rows = {0, N}.
+ *   - class sets are bit masks (bit c = class c); at most FMLP_MAX_CLASSES classes.
+ */
+#ifndef FEDMLP_B200_H_
+#define FEDMLP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMLP_ABI_VERSION 1
+#define FMLP_MAX_CLASSES 32   /* class bit masks are uint32_t                        */
+#define FMLP_MAX_SEGMENTS 64  /* segments (clients) per launch                        */
+#define FMLP_MAX_CLIENTS 64   /* client buffers folded per fedavg launch              */
+
+typedef enum fmlp_status {
+    FMLP_OK = 0,
+    FMLP_ERR_BAD_ARG = -1,     /* null pointer, negative size, K/S/C out of range       */
+    FMLP_ERR_UNSUPPORTED = -2, /* shape/alignment the kernels do not handle             */
+    FMLP_ERR_WORKSPACE = -3    /* workspace too small                                   */
+} fmlp_status;
+
+typedef void* fmlp_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ misc */
+int fmlp_abi_version(void);
+/* Human-readable text for a return code of any function in this header. */
+const char* fmlp_status_string(int code);
+/* Number of SMs of the current device (grid sizing is derived from it); <0 on error. */
+int fmlp_sm_count(void);
+
+/* ------------------------------------------------------------------ K1: FedAvg
+ * Replaces utils/FedAvg.py:7-14 `FedAvg` (and its twin `Fed_w` :16-23):
+ *     out[j] = ((((w_0[j]*n_0) + w_1[j]*n_1) + ...) + w_{K-1}[j]*n_{K-1}) / sum(n)
+ * evaluated per element in fp32 in exactly that order (separate round-to-nearest multiply and
+ * add, IEEE divide), so the result is bit-identical to the reference run on CPU tensors.
+ */
+enum {
+    FMLP_FEDAVG_DIVIDE = 1,     /* apply the final `/ divisor`                          */
+    FMLP_FEDAVG_ACCUMULATE = 2  /* start from out[j] instead of w_0[j]*n_0 (chains      */
+                                /* launches when K > FMLP_MAX_CLIENTS, still in order)  */
+};
+
+/* Flat form: every client is one contiguous fp32 buffer of P elements.
+ *   srcs    host array [K] of device pointers          weights  host array [K]          */
+int fmlp_fedavg_flat_f32(const float* const* srcs, const float* weights, int K, int64_t P,
+                         float divisor, int flags, float* out, fmlp_stream_t stream);
+
+/* int64 buffers (BatchNorm `num_batches_tracked`): reference multiplies/adds in int64 when the
+ * weights are integers and the true division then yields float32 (FedAvg.py:13).
+ * weights_integral != 0: acc(int64) = sum w_i[j]*(int64)n_i ; out = (float)acc / (float)divisor
+ * weights_integral == 0: acc(float) = (float)w_0[j]*(float)n_0 + ... ; out = acc / (float)divisor */
+int fmlp_fedavg_flat_i64(const int64_t* const* srcs, const double* weights, int K, int64_t J,
+                         double divisor, int weights_integral, int flags, float* out,
+                         fmlp_stream_t stream);
+
+/* Multi-tensor form: averages T separately-allocated tensors per client in ONE launch, reading
+ * the clients' state_dict storage in place (no packing copy).
+ *   src_table_dev  device array [T*K]: src_table_dev[t*K + i] = tensor t of client i
+ *   dst_table_dev  device array [T]  : output tensor t
+ *   numel_dev      device array [T]
+ *   chunk_tensor_dev / chunk_start_dev   device arrays [n_chunks]: chunk c covers elements
+ *        [chunk_start, chunk_start + FMLP_FEDAVG_CHUNK) of tensor chunk_tensor (clipped to numel)
+ *   weights        host array [K]                                                      */
+#define FMLP_FEDAVG_CHUNK 2048
+int fmlp_fedavg_multi_f32(const float* const* src_table_dev, float* const* dst_table_dev,
+                          const int64_t* numel_dev, const int32_t* chunk_tensor_dev,
+                          const int64_t* chunk_start_dev, int64_t n_chunks, int T,
+                          const float* weights, int K, float divisor, int flags,
+                          fmlp_stream_t stream);
+/* Same for T int64 tensors -> float32 outputs (one thread per element; tensors are scalars in
+ * practice).  elem_tensor_dev/elem_index_dev enumerate all J elements.                   */
+int fmlp_fedavg_multi_i64(const int64_t* const* src_table_dev, float* const* dst_table_dev,
+                          const int32_t* elem_tensor_dev, const int64_t* elem_index_dev,
+                          int64_t J, int T, const double* weights, int K, double divisor,
+                          int weights_integral, int flags, fmlp_stream_t stream);
+
+/* Prototype aggregation, replaces utils/FedAvg.py:72-93 `FedAvg_proto`:
+ *   out[2c+j] = (sum over clients i in act(c), in list order, of protos[i][2c+j]*n_i) / sum n_i
+ * protos  device [K][2C][D] (stacked client prototypes);  weights host [K];
+ * class_clients  host [C] bit masks over clients (bit i set = client i annotates class c),
+ *                K <= 64.  Empty act(c) gives 0/0 = NaN exactly like the reference.        */
+int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, const double* weights,
+                       const uint64_t* class_clients, float* out, fmlp_stream_t stream);
+
+/* ------------------------------------------------------------------ K2: class prototypes
+ * Replaces utils/local_training.py:973-1000 (stage 1) and :1208-1249 (stage 2):
+ * for every active class c of the segment, rows with labels[n,c]==0 are summed into row 2c and
+ * rows with labels[n,c]==1 into row 2c+1 (other label values contribute to neither), rows are
+ * counted, and for every class in the segment's `tcount` mask the number of confident
+ * predictions #{n : p<L or p>U}, p = sigmoid(logits[n,c]), is counted (:995-996,1239).
+ *
+ *   feat      [N_total, D] fp32, leading dimension ld_feat (elements), D % 4 == 0, 16-B aligned
+ *   labels    [N_total, C] fp32 (0/1)        logits  [N_total, C] fp32 or NULL (no t counts)
+ *   logits_are_probs != 0: `logits` already holds sigmoid outputs
+ *   seg_rows  host [S+1];  seg_active / seg_tcount  host [S] class masks
+ *   proto     [S, 2C, D] fp32 out: means (rows of non-active classes = 0)
+ *   cnt       [S, 2C] int32 out           tcnt  [S, C] int32 out (may be NULL iff logits NULL)
+ *   guard_empty != 0: an empty (class,label) group leaves its row 0 (stage 2, :1241-1248);
+ *                == 0: it is 0/0 = NaN (stage 1, :997-999)
+ * Deterministic: per-chunk partial sums are combined in a fixed order.                    */
+size_t fmlp_proto_ws_bytes(int64_t n_total, int D, int C, int S);
+int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, const float* labels,
+                         const float* logits, int logits_are_probs, int C, int S,
+                         const int64_t* seg_rows, const uint32_t* seg_active,
+                         const uint32_t* seg_tcount, float L, float U, int guard_empty,
+                         float* proto, int32_t* cnt, int32_t* tcnt, void* ws, size_t ws_bytes,
+                         fmlp_stream_t stream);
+
+/* ------------------------------------------------------------------ K3: tagging similarity
+ * Replaces utils/local_training.py:1052-1058 + CosineSimilarityFast.forward :1417-1435:
+ *   sim[c][n] = cos(f_n, P[2c]) - cos(f_n, P[2c+1]),   cos(f,p) = (f.p) * (1 / (|f|*|p|))
+ * for every class c in the row's segment `missing` mask, in ONE pass over feat.
+ *   proto   [2C, D] fp32 (the server-aggregated prototypes, shared by all segments)
+ *   sim     [C, N_total] fp32, class-major; rows of classes outside a segment's mask are
+ *           left untouched
+ *   mode    FMLP_SIM_PAIR: two cosines then subtract (op order of the reference)
+ *           FMLP_SIM_FOLDED: one dot against q_c = P[2c]/|P[2c]| - P[2c+1]/|P[2c+1]|
+ *           (half the FMAs; differs from PAIR by O(1e-7), inside the north_star waiver)    */
+enum { FMLP_SIM_PAIR = 0, FMLP_SIM_FOLDED = 1 };
+int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const float* proto, int C,
+                     int S, const int64_t* seg_rows, const uint32_t* seg_missing, float* sim,
+                     int64_t ld_sim, int mode, fmlp_stream_t stream);
+
+/* ------------------------------------------------------------------ K3b: selection
+ * Replaces utils/local_training.py:1061-1112 + utils/utils.py:24-35 (max_m_indices /
+ * min_n_indices).  Per (segment, missing class), over the candidate rows (tag == 0):
+ *   clean = {sim >= 0}, noise = {sim < 0}  (NaN in neither)
+ *   m = (int)(clean_frac*|clean|), k = (int)(noise_frac*|noise|)     (double arithmetic)
+ *   pick the m largest sims of `clean` and the k smallest of `noise`; equal sims are taken in
+ *   increasing row order (Python's stable sort); results are emitted in rank order.
+ * The picked rows are marked in `tag` (1 = clean/confident-negative, 2 = noise/confident-
+ * positive), which is also what makes them non-candidates next round (:1197-1204).
+ *   tag       [C, N_total] uint8, class-major, in/out
+ *   counts    [S, C, 4] int32 out: n_clean, n_noise, m, k   (zeros for non-missing classes)
+ *   sel       [S, C, 2, cap] int32 out: global row numbers, side 0 = clean, 1 = noise
+ *   cap       per-(segment,class,side) capacity; must be >= the largest possible m or k
+ * ws: fmlp_tag_select_ws_bytes(S, C, cap).                                                */
+size_t fmlp_tag_select_ws_bytes(int S, int C, int64_t cap);
+int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, int64_t ld_tag, int C,
+                    int S, const int64_t* seg_rows, const uint32_t* seg_missing,
+                    double clean_frac, double noise_frac, int32_t* counts, int32_t* sel,
+                    int64_t cap, void* ws, size_t ws_bytes, fmlp_stream_t stream);
+
+/* ------------------------------------------------------------------ K3c: label / mask fill
+ * Replaces DatasetSplit_pseudo.__getitem__ (utils/local_training.py:1456-1477) and
+ * `sup_cls = ~distill_cls` (:1173), for all rows at once:
+ *   active class  : y = labels_in, distill = 0
+ *   missing class : y = (tag == 2), distill = (tag == 0)
+ *   other classes : y = 0, distill = 0
+ *   sup = 1 - distill.      Any of y / distill / sup may be NULL.                          */
+int fmlp_mask_fill(const float* labels_in, const uint8_t* tag, int64_t ld_tag, int C, int S,
+                   const int64_t* seg_rows, const uint32_t* seg_active,
+                   const uint32_t* seg_missing, float* y, float* distill, float* sup,
+                   fmlp_stream_t stream);
+
+/* ------------------------------------------------------------------ K4: fused losses
+ * Stage 1, replaces utils/local_training.py:933-963 (+ utils/FedNoRo.py:16-22):
+ *   p_i = sigmoid(z_i)
+ *   loss = sum_{n, c in active} 0.5*(BCE(p1,y)+BCE(p2,y)) / (bs*A)
+ *        + sum_{n, c in missing} 0.5*((p1-p3)^2+(p2-p4)^2) / (bs*M)
+ *   BCE(p,y) = -(y*max(log p,-100) + (1-y)*max(log(1-p),-100))    (F.binary_cross_entropy)
+ *   dz = autograd of the above: BCE backward (p-y)/max((1-p)*p,1e-12) then sigmoid backward.
+ * `bs` is args.batch_size (NOT the number of rows B; :956-959).  A/M are popcounts of the masks.
+ * z1,z2 student logits (two views), z3,z4 frozen global model logits, all [B, C].
+ * loss: device float[1] out; dz1, dz2: [B, C] out (gradient of loss w.r.t. z1, z2).         */
+size_t fmlp_loss_ws_bytes(int64_t B, int C);
+int fmlp_loss_stage1_f32(const float* z1, const float* z2, const float* z3, const float* z4,
+                         const float* y, int64_t B, int C, uint32_t active, uint32_t missing,
+                         int bs, float* loss, float* dz1, float* dz2, void* ws,
+                         size_t ws_bytes, fmlp_stream_t stream);
+
+/* Stage 2, replaces utils/local_training.py:1171-1188:
+ *   variant FMLP_LOSS2_SUP      : loss = sum(BCE(p,y)*sup) / sum(sup)               (:1188, live)
+ *   variant FMLP_LOSS2_SUP_DIS  : loss = (sum(BCE*sup) + sum((p-pg)^2*distill))
+ *                                        / (sum(sup) + sum(distill))        (:1187, commented)
+ *   sup = 1 - distill (:1173), p = sigmoid(z), pg = sigmoid(zg).  zg may be NULL for _SUP.  */
+enum { FMLP_LOSS2_SUP = 0, FMLP_LOSS2_SUP_DIS = 1 };
+int fmlp_loss_stage2_f32(const float* z, const float* zg, const float* y, const float* distill,
+                         int64_t B, int C, int variant, float* loss, float* dz, void* ws,
+                         size_t ws_bytes, fmlp_stream_t stream);
+
+/* dz[i] *= *scale_dev  (upstream gradient of the scalar loss, read from device memory). */
+int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDMLP_B200_H_ */
