@@ -37,6 +37,7 @@ SIGNATURES = {
     "fmlp_abi_version": (_i, []),
     "fmlp_status_string": (C.c_char_p, [_i]),
     "fmlp_sm_count": (_i, []),
+    "fmlp_launch_count": (C.c_ulonglong, []),
     "fmlp_fedavg_flat_f32": (_i, [_p, _p, _i, _i64, _f, _i, _p, _p]),
     "fmlp_fedavg_flat_i64": (_i, [_p, _p, _i, _i64, _d, _i, _i, _p, _p]),
     "fmlp_fedavg_multi_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _i, _f, _i, _p]),

@@ -1,6 +1,10 @@
 // cabi.cu — ABI version / status strings / device queries of libfedmlp_b200.
 #include "common.cuh"
 
+namespace fmlp { unsigned long long g_launch_count = 0; }
+
+extern "C" unsigned long long fmlp_launch_count(void) { return __atomic_load_n(&fmlp::g_launch_count, __ATOMIC_RELAXED); }
+
 extern "C" int fmlp_abi_version(void) { return FMLP_ABI_VERSION; }
 
 extern "C" const char* fmlp_status_string(int code) {

@@ -28,9 +28,13 @@ inline int sm_count() {
     return cached[dev];
 }
 
+// Process-wide count of kernel launches issued by this library (bench.py reports it).
+extern unsigned long long g_launch_count;
+
 // Launch epilogue: surface launch-configuration errors as a positive cudaError_t.
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) __atomic_fetch_add(&g_launch_count, 1ull, __ATOMIC_RELAXED);
     return e == cudaSuccess ? FMLP_OK : (int)e;
 }
 

@@ -92,9 +92,19 @@ class TagBatch:
         the rows that are still candidates, tag-state update.  Returns (counts, sel, cap) device
         tensors: counts[s, c] = (n_clean, n_noise, m, k); sel[s, c, side, :m|k] = global rows in
         rank order."""
+        self.similarity(features, prototype, mode)
+        return self.select(clean_frac, noise_frac)
+
+    def similarity(self, features, prototype, mode="pair"):
+        """Fill self.sim [C, N] for every segment's missing classes (reference :1052-1058)."""
         if features.shape[0] != self.N:
             raise ValueError("feature rows != rows of the tag batch")
         tag_similarity(features, prototype, self.missing, self.seg_rows, out=self.sim, mode=mode)
+        return self.sim
+
+    def select(self, clean_frac=0.005, noise_frac=0.01):
+        """Sign split + top-fraction selection on self.sim among the candidate rows, and tag-state
+        update (reference :1061-1112, utils/utils.py:24-35)."""
         max_rows = max((self.seg_rows[s + 1] - self.seg_rows[s] for s in range(self.S)), default=0)
         cap = max(1, int(math.floor(max(clean_frac, noise_frac, 0.0) * max_rows)) + 1)
         cap = min(cap, max(max_rows, 1))

@@ -52,6 +52,8 @@ int fmlp_abi_version(void);
 const char* fmlp_status_string(int code);
 /* Number of SMs of the current device (grid sizing is derived from it); <0 on error. */
 int fmlp_sm_count(void);
+/* Kernel launches issued by this library since it was loaded (process-wide, monotonic). */
+unsigned long long fmlp_launch_count(void);
 
 /* ------------------------------------------------------------------ K1: FedAvg
  * Replaces utils/FedAvg.py:7-14 `FedAvg` (and its twin `Fed_w` :16-23):
