@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py — FedMLP round hot path (tag + loss + prototypes + FedAvg) on B200.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+A "step" is one pass of the per-round hot path over the clients resident on one GPU:
+  tag (similarity + selection + mask fill) over N_total x D features of the incoming global model,
+  stage-2 loss forward+backward over every client's rows, prototype/t construction over the
+  N_total x D features of the locally trained model, FedAvg over the K client parameter buffers.
+Workload at N=1 = BASELINE.json configs[1]: ICH 5-class DenseNet121, 8 clients on one B200,
+55,000 synthetic feature rows (6,875 per client), D=1024, P=7,042,629 fp32 parameters per client.
+With --gpus N>1 every rank holds its own 8 clients (weak scaling) and only FedAvg crosses GPUs
+(weighted partial sums + one NCCL all-reduce of the flat parameter buffer).
+
+Prints ONE JSON line (contract in the task statement): value = client-samples/s with inputs
+resident in HBM; e2e = the same through host buffers (pinned H2D of every input and D2H of every
+result inside the timed region); roofline = dominant kernel vs the measured HBM peak;
+cpu_baseline = the oracle port of the reference's CPU path timed on this box's cores.
+`--impl reference` times that CPU path alone (the reference is pure Python and cannot travel
+to the GPU box, so the arm is the oracle port — kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ICH_PREVALENCE = [0.015, 0.176, 0.128, 0.174, 0.230]
+METRIC = "client_samples_per_sec_per_fedmlp_round"
+UNIT = "client-samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clients-per-gpu", type=int, default=8)
+    ap.add_argument("--rows-per-client", type=int, default=6875)
+    ap.add_argument("--classes", type=int, default=5)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--sim-mode", default="pair", choices=["pair", "folded"])
+    ap.add_argument("--cpu-clients", type=int, default=2, help="clients in the bounded CPU-baseline sample")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------- workload
+def workload_name(a):
+    return (f"ICH {a.classes}-class DenseNet121, {a.clients_per_gpu} clients/GPU x {a.rows_per_client} rows, "
+            f"D={a.dim}: tag+loss+prototypes+FedAvg per round")
+
+
+def make_device_inputs(a, rank, dev):
+    """Seeded synthetic inputs of the named shapes, created on the device (setup, untimed)."""
+    import torch
+    from fedmlp_b200.shapes import count_params, densenet121_state_shapes
+    from fedmlp_b200.flat import layout_of
+
+    S, n, C, D = a.clients_per_gpu, a.rows_per_client, a.classes, a.dim
+    N = S * n
+    g = torch.Generator(device=dev).manual_seed(1037 + rank)
+    prev = torch.tensor(ICH_PREVALENCE if C == 5 else torch.linspace(0.02, 0.20, C).tolist(), device=dev)
+    labels = (torch.rand(N, C, generator=g, device=dev) < prev).float()
+    shift = torch.randn(C, D, generator=g, device=dev) * 0.25
+    feat_tag = torch.relu(torch.randn(N, D, generator=g, device=dev)) + torch.relu(labels @ shift)
+    feat_proto = torch.relu(torch.randn(N, D, generator=g, device=dev)) + torch.relu(labels @ shift)
+    logits = torch.randn(N, C, generator=g, device=dev) * 2
+    logits_glob = torch.randn(N, C, generator=g, device=dev) * 2
+    logits_proto = torch.randn(N, C, generator=g, device=dev) * 2
+    # server prototypes = masked means of the features (small, sign-mixed similarities as in practice)
+    rows = []
+    for c in range(C):
+        for v in (0.0, 1.0):
+            m = labels[:, c] == v
+            rows.append(feat_tag[m].mean(0) if bool(m.any()) else torch.zeros(D, device=dev))
+    proto = torch.stack(rows).contiguous()
+    shapes = densenet121_state_shapes(C)
+    P, J = count_params(shapes)
+    Ppad = sum((int(torch.Size(s).numel()) + 3) // 4 * 4 for s, d in shapes.values() if d == torch.float32)
+    base = torch.randn(Ppad, generator=g, device=dev) * 0.05
+    flats = [(base + 0.02 * torch.randn(Ppad, generator=g, device=dev)).contiguous() for _ in range(S)]
+    weights = [n] * S
+    return dict(N=N, P=P, J=J, Ppad=Ppad, labels=labels, feat_tag=feat_tag, feat_proto=feat_proto, logits=logits,
+                logits_glob=logits_glob, logits_proto=logits_proto, proto=proto, flats=flats, weights=weights)
+
+
+def alg_bytes(a, inp):
+    """Algorithmic bytes per launch."""
+    N, D, C, K, P = inp["N"], a.dim, a.classes, a.clients_per_gpu, inp["Ppad"]
+    M = C - 1
+    return {
+        "sim": 4 * N * D + 4 * 2 * C * D + 4 * M * N,
+        "proto": 4 * N * D + 4 * N * C * 2 + 4 * 2 * C * D * K,
+        "fedavg": (K + 1) * 4 * P,
+        "loss": 5 * 4 * N * C,
+        "select_fill": 4 * M * N * 4 + 2 * 4 * N * C,
+    }
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.path = f"/tmp/fedmlp_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+            out["sm_mhz"] = statistics.median(busy)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------- CPU path (oracle port)
+def cpu_round_sample(a, n_clients, seed=1037):
+    """Build the bounded CPU sample: `n_clients` clients of the workload + K state_dicts."""
+    import torch
+    from oracle import fedmlp_oracle as O
+    from fedmlp_b200.shapes import densenet121_state_shapes, synth_state_dict
+
+    C, D, n = a.classes, a.dim, a.rows_per_client
+    clients = []
+    for k in range(n_clients):
+        feat, labels, logits = O.synth_client(n, D, C, seed=seed + k)
+        feat2, _, logits2 = O.synth_client(n, D, C, seed=seed + 100 + k)
+        clients.append(dict(feat=feat, labels=labels, logits=logits, feat2=feat2, logits2=logits2,
+                            zg=torch.randn(n, C, generator=torch.Generator().manual_seed(seed + 200 + k)) * 2,
+                            active=[k % C], missing=[c for c in range(C) if c != k % C],
+                            state=O.TaggingState(list(range(n)), [c for c in range(C) if c != k % C])))
+    proto = O.synth_prototypes(clients[0]["feat"], clients[0]["labels"])
+    shapes = densenet121_state_shapes(C)
+    base = synth_state_dict(shapes, seed)
+    sds = [synth_state_dict(shapes, seed + 1 + k, base=base, counter=100 + k) for k in range(a.clients_per_gpu)]
+    return dict(clients=clients, proto=proto, sds=sds, weights=[n] * a.clients_per_gpu)
+
+
+def cpu_round_step(a, sample):
+    """One pass of the reference's CPU path (oracle port) over the sample; returns (t_clients, t_fedavg)."""
+    import torch
+    from oracle import fedmlp_oracle as O
+
+    t0 = time.perf_counter()
+    for cl in sample["clients"]:
+        # tag: similarity + python-sorted selection (utils/utils.py:24-35) + label/mask fill
+        cl["state"].traindata_idx = [[] for _ in cl["state"].traindata_idx]
+        cl["state"].step(cl["feat"], sample["proto"], 0.005, 0.01, python_sort=True)
+        tgt, dis = O.mask_fill(cl["labels"].numpy(), cl["state"].dataset_idx, cl["active"], cl["missing"],
+                               cl["state"].traindata_idx)
+        # stage-2 loss forward + backward over the client's rows
+        O.loss_and_grads(lambda z, zg, y, d: O.stage2_loss(z, zg, y, d), cl["logits"], cl["zg"],
+                         torch.from_numpy(tgt), torch.from_numpy(dis), n_grad=1)
+        # prototypes + t
+        O.prototype_build(cl["feat2"], cl["labels"], cl["logits2"], cl["active"], cl["missing"], 0.3, 0.7, True)
+    t1 = time.perf_counter()
+    O.fedavg(sample["sds"], sample["weights"])
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def run_cpu_arm(a, steps, warmup):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = cpu_round_sample(a, a.cpu_clients)
+    for _ in range(warmup):
+        cpu_round_step(a, sample)
+    tc, tf = [], []
+    for _ in range(steps):
+        c, f = cpu_round_step(a, sample)
+        tc.append(c); tf.append(f)
+    scale = a.clients_per_gpu / a.cpu_clients
+    t_step = statistics.mean(tc) * scale + statistics.mean(tf)
+    n_total = a.clients_per_gpu * a.rows_per_client
+    P = 7042629 if a.classes == 5 else None
+    return dict(value=n_total / t_step, t_step=t_step, t_clients=statistics.mean(tc), t_fedavg=statistics.mean(tf),
+                cores=cores, P=P,
+                sample=(f"{a.cpu_clients} of {a.clients_per_gpu} clients ({a.cpu_clients * a.rows_per_client} rows) through "
+                        f"tag+mask-fill+loss+prototypes (time x{scale:g}) + FedAvg over all {a.clients_per_gpu} "
+                        f"DenseNet121 state_dicts (727 tensors), {steps} steps after {warmup} warm-up"))
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    # keep the whole run within a few minutes whatever K/W the driver passes
+    budget_steps = 40
+    if steps + warmup > budget_steps:
+        warmup = min(warmup, 5)
+        steps_run = budget_steps - warmup
+    else:
+        steps_run = steps
+    r = run_cpu_arm(a, steps_run, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "steps_executed": steps_run},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "fedavg_gbs": ((a.clients_per_gpu + 1) * 4 * r["P"] / r["t_fedavg"] / 1e9) if r["P"] else None,
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(kernel):
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+
+    import fedmlp_b200 as F
+    from fedmlp_b200 import _cabi as cabi
+    from fedmlp_b200.round import ClientShard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = cabi.load()
+
+    inp = make_device_inputs(a, rank, dev)
+    S, C = a.clients_per_gpu, a.classes
+    shard = ClientShard([a.rows_per_client] * S, C, [[(rank * S + k) % C] for k in range(S)], device=dev,
+                        sim_mode=a.sim_mode)
+    fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
+    if world > 1:
+        total_w = float(sum(inp["weights"]) * world)
+        w_norm = [w / total_w for w in inp["weights"]]          # pre-normalised: all-reduce yields the mean
+
+    def step(timers=None):
+        if world == 1:
+            return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
+                                        inp["feat_proto"], inp["logits_proto"], inp["flats"], inp["weights"],
+                                        timers=timers, fedavg_out=fed_out)
+        r = shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
+                                 inp["feat_proto"], inp["logits_proto"], inp["flats"], w_norm, timers=timers,
+                                 fedavg_out=fed_out, divide=False)
+        dist.all_reduce(fed_out)
+        if timers is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            r.events["allreduce"] = e
+        return r
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(a.warmup, 3)):
+        step()
+    fence()
+    launches0 = lib.fmlp_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    results = []          # only the per-stage events are kept (holding outputs would defeat the allocator)
+    ev0.record()
+    for _ in range(a.steps):
+        results.append(step(timers=True).events)
+    ev1.record()
+    fence()
+    launches = lib.fmlp_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+
+    # per-kernel device times from the events recorded inside the timed steps
+    order = ["start", "sim", "select_fill", "loss", "proto", "fedavg"] + (["allreduce"] if world > 1 else [])
+    per = {k: [] for k in order[1:]}
+    for evs in results:
+        for p, q in zip(order[:-1], order[1:]):
+            per[q].append(evs[p].elapsed_time(evs[q]))
+    kms = {k: statistics.mean(v) for k, v in per.items()}
+    ab = alg_bytes(a, inp)
+    peak, peak_src = peak_hbm()
+    kernels = {}
+    for k in ("sim", "proto", "fedavg", "loss", "select_fill"):
+        gbs = ab[k] / (kms[k] * 1e-3) / 1e9
+        kernels[k] = {"ms": round(kms[k], 5), "alg_bytes": ab[k], "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+    if world > 1:
+        kernels["allreduce"] = {"ms": round(kms["allreduce"], 5), "alg_bytes": 4 * inp["Ppad"],
+                                "bus_gbs": round(2 * (world - 1) / world * 4 * inp["Ppad"] / (kms["allreduce"] * 1e-3) / 1e9, 1)}
+    dom = max(("sim", "proto", "fedavg"), key=lambda k: kms[k])
+    dom_names = {"sim": "tag_sim_kernel", "proto": "proto_accum_kernel", "fedavg": "fedavg_flat_kernel"}
+    roofline = {"kernel": dom_names[dom], "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": traffic_from_profiles(dom_names[dom]),
+                "peak_source": peak_src, "alg_bytes_per_launch": ab[dom], "avg_launch_ms": round(kms[dom], 5)}
+    n_total_all = inp["N"] * world
+    value = n_total_all / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> round -> D2H of every result, per step
+    e2e = None
+    if not a.skip_e2e:
+        e2e = run_e2e(a, inp, shard, step, fed_out, world, dev)
+    clocks = sampler.stop() if sampler else None
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.skip_cpu_baseline:
+            r = run_cpu_arm(a, steps=3, warmup=1)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                   "ms_per_step": r["t_step"] * 1e3, "fedavg_gbs": (S + 1) * 4 * inp["P"] / r["t_fedavg"] / 1e9}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "clients_per_gpu": S, "rows_per_client": a.rows_per_client,
+                       "feature_dim": a.dim, "classes": C, "params_per_client": inp["P"], "sim_mode": a.sim_mode,
+                       "l2": f"inputs larger than L2: {round((ab['sim'] + ab['proto'] + ab['fedavg']) / 1e6)} MB streamed per step vs 126 MB L2, no flush needed",
+                       "parallelism": f"clients sharded over {world} GPU(s); FedAvg = local weighted partial + NCCL all-reduce" if world > 1 else "single GPU"},
+            "fedavg_gbs": kernels["fedavg"]["gbs"],
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(a, inp, shard, step_fn, fed_out, world, dev):
+    """Same round through host buffers: every input tensor is copied from pinned host memory and
+    every result is read back to pinned host memory inside the timed region, every step."""
+    import torch
+    import torch.distributed as dist
+
+    names = ["feat_tag", "logits", "logits_glob", "labels", "feat_proto", "logits_proto", "proto"]
+    host = {k: inp[k].cpu().pin_memory() for k in names}
+    host_flats = [f.cpu().pin_memory() for f in inp["flats"]]
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(f.numel() * 4 for f in host_flats)
+    out_host = {}
+    d2h_holder = [0]
+
+    def e2e_step():
+        for k in names:
+            inp[k].copy_(host[k], non_blocking=True)
+        for d, h in zip(inp["flats"], host_flats):
+            d.copy_(h, non_blocking=True)
+        r = step_fn()
+        outs = {"counts": r.counts, "sel": r.sel, "losses": r.losses, "dz": r.dz, "proto": r.protos.proto,
+                "cnt": r.protos.cnt, "tcnt": r.protos.tcnt, "global": fed_out}
+        n = 0
+        for k, v in outs.items():
+            if k not in out_host or out_host[k].shape != v.shape:
+                out_host[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            out_host[k].copy_(v, non_blocking=True)
+            n += v.numel() * v.element_size()
+        d2h_holder[0] = n
+        torch.cuda.synchronize()     # the caller needs the results before the next round
+
+    steps = a.e2e_steps or min(a.steps, 20)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+    return {"value": inp["N"] * world / (ms_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h_holder[0]), "ms_per_step": ms_step, "steps": steps,
+            "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps}
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,31 @@ def _scale_by(dz, grad_out):
     return dz
 
 
+def launch_stage1(z1, z2, z3, z4, y, active_mask, missing_mask, batch_size, loss_out, dz1_out, dz2_out):
+    """Raw launch of fmlp_loss_stage1_f32 into caller-provided outputs (all contiguous fp32 CUDA)."""
+    B, C = z1.shape
+    dev = z1.device
+    lib = cabi.lib()
+    with torch.cuda.device(dev):
+        ws = workspace("loss", lib.fmlp_loss_ws_bytes(B, C), dev)
+        cabi.check(lib.fmlp_loss_stage1_f32(z1.data_ptr(), z2.data_ptr(), z3.data_ptr(), z4.data_ptr(),
+                                            y.data_ptr(), B, C, active_mask, missing_mask, int(batch_size),
+                                            loss_out.data_ptr(), dz1_out.data_ptr(), dz2_out.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), cabi.stream_ptr(dev)), "fmlp_loss_stage1_f32")
+
+
+def launch_stage2(z, zg, y, distill, variant, loss_out, dz_out):
+    """Raw launch of fmlp_loss_stage2_f32 into caller-provided outputs (all contiguous fp32 CUDA)."""
+    B, C = z.shape
+    dev = z.device
+    lib = cabi.lib()
+    with torch.cuda.device(dev):
+        ws = workspace("loss", lib.fmlp_loss_ws_bytes(B, C), dev)
+        cabi.check(lib.fmlp_loss_stage2_f32(z.data_ptr(), None if zg is None else zg.data_ptr(), y.data_ptr(),
+                                            distill.data_ptr(), B, C, variant, loss_out.data_ptr(), dz_out.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), cabi.stream_ptr(dev)), "fmlp_loss_stage2_f32")
+
+
 class _Stage1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z1, z2, z3, z4, y, active_mask, missing_mask, batch_size):
@@ -47,13 +72,7 @@ class _Stage1(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         dz1 = torch.empty_like(z1)
         dz2 = torch.empty_like(z2)
-        lib = cabi.lib()
-        with torch.cuda.device(dev):
-            ws = workspace("loss", lib.fmlp_loss_ws_bytes(B, C), dev)
-            cabi.check(lib.fmlp_loss_stage1_f32(z1.data_ptr(), z2.data_ptr(), z3.data_ptr(), z4.data_ptr(),
-                                                y.data_ptr(), B, C, active_mask, missing_mask, int(batch_size),
-                                                loss.data_ptr(), dz1.data_ptr(), dz2.data_ptr(), ws.data_ptr(),
-                                                ws.numel(), cabi.stream_ptr(dev)), "fmlp_loss_stage1_f32")
+        launch_stage1(z1, z2, z3, z4, y, active_mask, missing_mask, batch_size, loss, dz1, dz2)
         ctx.save_for_backward(dz1, dz2)
         return loss.reshape(())
 
@@ -72,13 +91,7 @@ class _Stage2(torch.autograd.Function):
         dev = z.device
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         dz = torch.empty_like(z)
-        lib = cabi.lib()
-        with torch.cuda.device(dev):
-            ws = workspace("loss", lib.fmlp_loss_ws_bytes(B, C), dev)
-            cabi.check(lib.fmlp_loss_stage2_f32(z.data_ptr(), None if zg is None else zg.data_ptr(), y.data_ptr(),
-                                                distill.data_ptr(), B, C, variant, loss.data_ptr(), dz.data_ptr(),
-                                                ws.data_ptr(), ws.numel(), cabi.stream_ptr(dev)),
-                       "fmlp_loss_stage2_f32")
+        launch_stage2(z, zg, y, distill, variant, loss, dz)
         ctx.save_for_backward(dz)
         return loss.reshape(())
 
