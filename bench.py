@@ -301,6 +301,7 @@ def gpu_arm(a):
     S, C = a.clients_per_gpu, a.classes
     shard = ClientShard([a.rows_per_client] * S, C, [[(rank * S + k) % C] for k in range(S)], device=dev,
                         sim_mode=a.sim_mode)
+    shard.keep_history = False      # host-list bookkeeping (two small device copies per round) is off the hot path
     fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
     if world > 1:
         total_w = float(sum(inp["weights"]) * world)

@@ -135,93 +135,119 @@ __global__ void __launch_bounds__(kLossThreads) loss_stage1_kernel(const __grid_
 
 struct Loss2Args {
     const float *z, *zg, *y, *distill;
-    float *loss, *dz;
+    float *loss, *dz;   // loss[S]
     float* ws;
-    int64_t n;
+    int64_t el_per_cta;  // elements handled by one CTA (contiguous range)
+    int C;
     int variant;
+    SegTable seg;        // rows prefix per segment (client); masks unused
 };
 
+// Segmented stage-2 loss: every segment (client) has its own denominator sum(sup) and its own
+// scalar loss, all in ONE cooperative launch.  CTA b owns the contiguous element range
+// [b*E, (b+1)*E); the part of it inside segment s is reduced on its own and published in
+// workspace slot b + s (injective because both b and s grow along the range), so the partials of
+// a segment are combined in CTA order -> deterministic, no atomics, nothing to pre-zero.
 __global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_constant__ Loss2Args a) {
     __shared__ float s_red[32];
     __shared__ int s_redi[32];
-    __shared__ float s_den;
+    __shared__ float s_den[2];
     cg::grid_group grid = cg::this_grid();
     int* wsi = reinterpret_cast<int*>(a.ws);
-    const int64_t stride = (int64_t)gridDim.x * kLossThreads * kLossUnroll;
-    const int64_t first = (int64_t)blockIdx.x * kLossThreads * kLossUnroll + threadIdx.x;
+    const int S = a.seg.S;
+    const int64_t n_el = a.seg.rows[S] * a.C;
+    const int64_t e_begin = (int64_t)blockIdx.x * a.el_per_cta;
+    const int64_t e_end = min(n_el, e_begin + a.el_per_cta);
+    const int s_first = e_begin < n_el ? find_segment(a.seg.rows, S, e_begin / a.C) : S;
 
-    // ---- phase 1: denominator.  sup/distill are 0/1 masks, so the sums are exact integers ----
-    int n_dis = 0, n_all = 0;
-    for (int64_t base = first; base < a.n; base += stride) {
-#pragma unroll
-        for (int u = 0; u < kLossUnroll; ++u) {
-            const int64_t e = base + (int64_t)u * kLossThreads;
-            if (e < a.n) { n_dis += (a.distill[e] != 0.f) ? 1 : 0; n_all += 1; }
-        }
+    // ---- phase 1: per (CTA, segment) count of distilled entries; sup/distill are 0/1 masks, so
+    //      the denominators are exact integers
+    for (int s = s_first; s < S; ++s) {
+        const int64_t lo = max(e_begin, a.seg.rows[s] * a.C), hi = min(e_end, a.seg.rows[s + 1] * a.C);
+        if (lo >= e_end) break;
+        int n_dis = 0;
+        for (int64_t e = lo + threadIdx.x; e < hi; e += kLossThreads) n_dis += (a.distill[e] != 0.f) ? 1 : 0;
+        const int b_dis = block_sum_i(n_dis, s_redi);
+        if (threadIdx.x == 0) wsi[2 * kLossMaxGrid + blockIdx.x + s] = b_dis;
     }
-    const int b_dis = block_sum_i(n_dis, s_redi);
-    const int b_all = block_sum_i(n_all, s_redi);
-    if (threadIdx.x == 0) { wsi[2 * kLossMaxGrid + blockIdx.x] = b_dis; wsi[3 * kLossMaxGrid + blockIdx.x] = b_all; }
     grid.sync();
-    {
-        int td = 0, ta = 0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += kLossThreads) { td += wsi[2 * kLossMaxGrid + b]; ta += wsi[3 * kLossMaxGrid + b]; }
+
+    // ---- phase 2: numerators + gradient, segment by segment -----------------------------------
+    for (int s = s_first; s < S; ++s) {
+        const int64_t seg_lo = a.seg.rows[s] * a.C, seg_hi = a.seg.rows[s + 1] * a.C;
+        const int64_t lo = max(e_begin, seg_lo), hi = min(e_end, seg_hi);
+        if (lo >= e_end) break;
+        if (hi <= lo) continue;  // empty segment
+        // denominator of segment s: add the counts of every CTA that touches it, in CTA order
+        const int b0 = (int)(seg_lo / a.el_per_cta), b1 = (int)((seg_hi - 1) / a.el_per_cta);
+        int td = 0;
+        for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) td += wsi[2 * kLossMaxGrid + b + s];
         td = block_sum_i(td, s_redi);
-        ta = block_sum_i(ta, s_redi);
         if (threadIdx.x == 0) {
-            const float sum_dis = (float)td, sum_sup = (float)(ta - td);
+            const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
             // :1188  sup_cls.sum()          :1187  sup_cls.sum() + distill_cls.sum()
-            s_den = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+            s_den[0] = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
         }
         __syncthreads();
-    }
-    const float den = s_den;
-    const float g = __fdiv_rn(1.f, den);  // d loss / d numerator
-
-    // ---- phase 2: numerators + gradient -----------------------------------------------------
-    float num_sup = 0.f, num_dis = 0.f;
-    for (int64_t base = first; base < a.n; base += stride) {
-        float vz[kLossUnroll], vg[kLossUnroll], vy[kLossUnroll], vd[kLossUnroll];
+        const float den = s_den[0];
+        const float g = __fdiv_rn(1.f, den);  // d loss / d numerator
+        float num_sup = 0.f, num_dis = 0.f;
+        for (int64_t base = lo + threadIdx.x; base < hi; base += (int64_t)kLossThreads * kLossUnroll) {
+            float vz[kLossUnroll], vg[kLossUnroll], vy[kLossUnroll], vd[kLossUnroll];
 #pragma unroll
-        for (int u = 0; u < kLossUnroll; ++u) {
-            const int64_t e = base + (int64_t)u * kLossThreads;
-            const bool ok = e < a.n;
-            vz[u] = ok ? a.z[e] : 0.f;
-            vy[u] = ok ? a.y[e] : 0.f;
-            vd[u] = ok ? a.distill[e] : 0.f;
-            vg[u] = (ok && a.variant == FMLP_LOSS2_SUP_DIS) ? a.zg[e] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < kLossUnroll; ++u) {
-            const int64_t e = base + (int64_t)u * kLossThreads;
-            if (e >= a.n) continue;
-            const float p = sigmoid_ref(vz[u]);
-            const float dist = vd[u];
-            const float sup = (dist != 0.f) ? 0.f : 1.f;  // (~distill_cls.bool()).float()  (:1173)
-            // loss_sup * sup_cls, backward: (g * sup) into BCE backward
-            num_sup += __fmul_rn(bce_fwd(p, vy[u]), sup);
-            float gp = bce_bwd(__fmul_rn(g, sup), p, vy[u]);
-            if (a.variant == FMLP_LOSS2_SUP_DIS) {
-                const float pg = sigmoid_ref(vg[u]);
-                const float d = __fsub_rn(p, pg);
-                num_dis += __fmul_rn(__fmul_rn(d, d), dist);
-                gp = __fadd_rn(gp, mse_bwd(__fmul_rn(g, dist), p, pg));
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int64_t e = base + (int64_t)u * kLossThreads;
+                const bool ok = e < hi;
+                vz[u] = ok ? a.z[e] : 0.f;
+                vy[u] = ok ? a.y[e] : 0.f;
+                vd[u] = ok ? a.distill[e] : 0.f;
+                vg[u] = (ok && a.variant == FMLP_LOSS2_SUP_DIS) ? a.zg[e] : 0.f;
             }
-            a.dz[e] = sigmoid_bwd(gp, p);
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int64_t e = base + (int64_t)u * kLossThreads;
+                if (e >= hi) continue;
+                const float p = sigmoid_ref(vz[u]);
+                const float dist = vd[u];
+                const float sup = (dist != 0.f) ? 0.f : 1.f;  // (~distill_cls.bool()).float()  (:1173)
+                // loss_sup * sup_cls, backward: (g * sup) into BCE backward
+                num_sup += __fmul_rn(bce_fwd(p, vy[u]), sup);
+                float gp = bce_bwd(__fmul_rn(g, sup), p, vy[u]);
+                if (a.variant == FMLP_LOSS2_SUP_DIS) {
+                    const float pg = sigmoid_ref(vg[u]);
+                    const float d = __fsub_rn(p, pg);
+                    num_dis += __fmul_rn(__fmul_rn(d, d), dist);
+                    gp = __fadd_rn(gp, mse_bwd(__fmul_rn(g, dist), p, pg));
+                }
+                a.dz[e] = sigmoid_bwd(gp, p);
+            }
         }
+        const float bn_sup = block_sum(num_sup, s_red);
+        const float bn_dis = block_sum(num_dis, s_red);
+        if (threadIdx.x == 0) { a.ws[blockIdx.x + s] = bn_sup; a.ws[kLossMaxGrid + blockIdx.x + s] = bn_dis; }
+        __syncthreads();  // s_den reuse
     }
-    const float bn_sup = block_sum(num_sup, s_red);
-    const float bn_dis = block_sum(num_dis, s_red);
-    if (threadIdx.x == 0) { a.ws[blockIdx.x] = bn_sup; a.ws[kLossMaxGrid + blockIdx.x] = bn_dis; }
     grid.sync();
-    if (blockIdx.x == 0) {
-        float ts = 0.f, td = 0.f;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += kLossThreads) { ts += a.ws[b]; td += a.ws[kLossMaxGrid + b]; }
+
+    // ---- final: one CTA per segment (round-robin) adds the partials in CTA order ------------
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const int64_t seg_lo = a.seg.rows[s] * a.C, seg_hi = a.seg.rows[s + 1] * a.C;
+        float ts = 0.f, tdis = 0.f;
+        int td = 0;
+        if (seg_hi > seg_lo) {
+            const int b0 = (int)(seg_lo / a.el_per_cta), b1 = (int)((seg_hi - 1) / a.el_per_cta);
+            for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) {
+                ts += a.ws[b + s]; tdis += a.ws[kLossMaxGrid + b + s]; td += wsi[2 * kLossMaxGrid + b + s];
+            }
+        }
         ts = block_sum(ts, s_red);
-        td = block_sum(td, s_red);
+        tdis = block_sum(tdis, s_red);
+        td = block_sum_i(td, s_redi);
         if (threadIdx.x == 0) {
-            const float num = a.variant == FMLP_LOSS2_SUP ? ts : __fadd_rn(ts, td);
-            a.loss[0] = __fdiv_rn(num, den);
+            const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
+            const float den = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+            const float num = a.variant == FMLP_LOSS2_SUP ? ts : __fadd_rn(ts, tdis);
+            a.loss[s] = __fdiv_rn(num, den);
         }
     }
 }
@@ -285,24 +311,49 @@ extern "C" int fmlp_loss_stage1_f32(const float* z1, const float* z2, const floa
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 
-extern "C" int fmlp_loss_stage2_f32(const float* z, const float* zg, const float* y, const float* distill,
-                                    int64_t B, int C, int variant, float* loss, float* dz, void* ws,
-                                    size_t ws_bytes, fmlp_stream_t stream) {
-    if (!z || !y || !distill || !loss || !dz || !ws || B < 0 || C < 1 || C > FMLP_MAX_CLASSES)
-        return FMLP_ERR_BAD_ARG;
+static int launch_loss2(const float* z, const float* zg, const float* y, const float* distill, int C, int S,
+                        const int64_t* seg_rows, int variant, float* loss, float* dz, void* ws, size_t ws_bytes,
+                        fmlp_stream_t stream) {
+    if (!z || !y || !distill || !loss || !dz || !ws || C < 1 || C > FMLP_MAX_CLASSES) return FMLP_ERR_BAD_ARG;
     if (variant != FMLP_LOSS2_SUP && variant != FMLP_LOSS2_SUP_DIS) return FMLP_ERR_BAD_ARG;
     if (variant == FMLP_LOSS2_SUP_DIS && !zg) return FMLP_ERR_BAD_ARG;
-    if (ws_bytes < fmlp_loss_ws_bytes(B, C)) return FMLP_ERR_WORKSPACE;
+    if (ws_bytes < fmlp_loss_ws_bytes(0, C)) return FMLP_ERR_WORKSPACE;
     Loss2Args a;
-    a.z = z; a.zg = zg; a.y = y; a.distill = distill; a.loss = loss; a.dz = dz; a.ws = (float*)ws;
-    a.n = B * C; a.variant = variant;
-    int grid = 1;
-    int rc = coop_grid(loss_stage2_kernel, a.n, &grid);
+    int rc = fill_seg_table(a.seg, S, seg_rows, nullptr, nullptr);
     if (rc != FMLP_OK) return rc;
+    a.z = z; a.zg = zg; a.y = y; a.distill = distill; a.loss = loss; a.dz = dz; a.ws = (float*)ws;
+    a.C = C; a.variant = variant;
+    const int64_t n_el = seg_rows[S] * C;
+    int grid = 1;
+    rc = coop_grid(loss_stage2_kernel, n_el, &grid);
+    if (rc != FMLP_OK) return rc;
+    // two grid barriers + per-segment slot sums: fewer, fatter CTAs are cheaper here (one per SM)
+    const int sms = sm_count();
+    if (sms > 0 && grid > sms) grid = sms;
+    if (grid > kLossMaxGrid - FMLP_MAX_SEGMENTS) grid = kLossMaxGrid - FMLP_MAX_SEGMENTS;  // slots b + s
+    const int64_t tile = (int64_t)kLossThreads * kLossUnroll;
+    int64_t epc = (n_el + grid - 1) / grid;
+    epc = (epc + tile - 1) / tile * tile;
+    if (epc < tile) epc = tile;
+    a.el_per_cta = epc;
     void* args[] = {(void*)&a};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)loss_stage2_kernel, dim3(grid), dim3(kLossThreads),
                                                 args, 0, (cudaStream_t)stream);
     return e == cudaSuccess ? launch_status() : (int)e;
+}
+
+extern "C" int fmlp_loss_stage2_f32(const float* z, const float* zg, const float* y, const float* distill,
+                                    int64_t B, int C, int variant, float* loss, float* dz, void* ws,
+                                    size_t ws_bytes, fmlp_stream_t stream) {
+    if (B < 0) return FMLP_ERR_BAD_ARG;
+    const int64_t rows[2] = {0, B};
+    return launch_loss2(z, zg, y, distill, C, 1, rows, variant, loss, dz, ws, ws_bytes, stream);
+}
+
+extern "C" int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const float* y, const float* distill,
+                                        int C, int S, const int64_t* seg_rows, int variant, float* loss,
+                                        float* dz, void* ws, size_t ws_bytes, fmlp_stream_t stream) {
+    return launch_loss2(z, zg, y, distill, C, S, seg_rows, variant, loss, dz, ws, ws_bytes, stream);
 }
 
 extern "C" int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream) {

@@ -4,52 +4,58 @@
 // Replaces utils/local_training.py:973-1000 (end of stage 1) and :1208-1249 (every stage-2
 // round).  The reference walks the data in batches of 128 rows and, per active class, does
 // where/gather/sum/.cpu() twice plus one .item() per missing class (3+ host syncs per batch).
-// Here the [N, D] features are streamed once: a CTA owns the full width of a chunk of rows
-// (thread <-> float4 column, so every row is one coalesced request per warp), keeps the
-// label-0 / label-1 running sums of up to 4 active classes in registers, and emits one partial
-// per chunk; a second tiny kernel adds the partials of a segment in chunk order (deterministic,
-// no float atomics) and applies the guarded divide.  Algorithmic bytes: 4*N*D + 8*N*C + 8*C*D.
+// Here the [N, D] features are streamed once.  Thread <-> float4 column, so a CTA reads whole
+// rows (one coalesced 512-B request per warp per row) and keeps the label-0 / label-1 running
+// sums of up to 4 active classes in registers.
+//
+// Work split (r01 ncu: the first version launched 1.46 waves of chunk-CTAs and lost 30 % to the
+// tail): the grid is exactly the number of co-resident CTAs and CTA b owns the contiguous row
+// range [b*rows_per_cta, (b+1)*rows_per_cta) -> one balanced wave.  Where a range crosses a
+// segment (client) boundary the CTA flushes and starts a new partial; the partial of (CTA b,
+// segment s) lives in slot b + s (injective, both grow along the rows).  Row loads are ping-pong
+// buffered (4 + 4 rows in flight per thread) because B200 HBM needs ~100 KB in flight per SM.
+// Label and t counts are per-slot partials too, so nothing is zeroed and nothing is atomic on
+// global memory; a second small kernel adds the slots of each segment in CTA order
+// (deterministic) and applies the guarded divide.  Algorithmic bytes: 4*N*D + 8*N*C + 8*C*D.
 #include "common.cuh"
 
 namespace fmlp {
 
 constexpr int kProtoMaxActive = 4;  // active classes accumulated per pass (annotation_num is 1)
-constexpr int kProtoUnroll = 8;     // rows in flight per thread
-
-// Chunk height: large enough that the partial traffic (2*NA*D*4 B per chunk, written and read
-// once) stays ~3 % of the feature bytes, small enough that >= 2 CTAs per SM exist.
-static inline int proto_chunk_rows(int64_t n_total) {
-    if (n_total >= 37888) return 128;  // 256 rows * 148 SMs
-    if (n_total >= 14208) return 64;
-    return 32;
-}
+constexpr int kProtoUnroll = 4;     // rows per batch; two batches in flight (ping-pong)
+constexpr int kProtoMaxCtasPerSm = 8;
 
 struct ProtoArgs {
     const float* feat;
     const float* labels;
     const float* logits;
-    float* partial;   // [n_items][NA][2][D]
-    int32_t* cnt;     // [S][2C]
-    int32_t* tcnt;    // [S][C]
+    float* partial;    // [slots][NA][2][D]
+    int32_t* pcount;   // [slots][2*kProtoMaxActive + FMLP_MAX_CLASSES]
     int64_t ld_feat;
-    int64_t item_base[FMLP_MAX_SEGMENTS + 1];  // prefix of chunk counts per segment
-    SegTable seg;     // mask_a = active classes (restricted to this pass), mask_b = tcount classes
+    int64_t rows_per_cta;
+    SegTable seg;      // mask_a = active classes (restricted to this pass), mask_b = tcount classes
     float L, U;
-    int D, C, chunk_rows, logits_are_probs, count_labels;
+    int D, C, logits_are_probs, do_t;
 };
+constexpr int kProtoCountStride = 2 * kProtoMaxActive + FMLP_MAX_CLASSES;
 
 template <int NA>
-__global__ void __launch_bounds__(512) proto_accum_kernel(const __grid_constant__ ProtoArgs a) {
+__global__ void __launch_bounds__(512, NA == 1 ? 2 : 1) proto_accum_kernel(const __grid_constant__ ProtoArgs a) {
     __shared__ int s_t[FMLP_MAX_CLASSES];
     const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     const bool col_ok = col < a.D;
-    const int64_t n_items = a.item_base[a.seg.S];
+    const int S = a.seg.S;
+    const int64_t n_total = a.seg.rows[S];
+    const int64_t cta_begin = (int64_t)blockIdx.x * a.rows_per_cta;
+    const int64_t cta_end = min(n_total, cta_begin + a.rows_per_cta);
+    if (cta_begin >= n_total) return;
+    int s = find_segment(a.seg.rows, S, cta_begin);
+    int64_t row = cta_begin;
 
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        // segment of this item (item_base is a prefix array like seg.rows)
-        const int s = find_segment(a.item_base, a.seg.S, item);
-        const int64_t r_begin = a.seg.rows[s] + (item - a.item_base[s]) * a.chunk_rows;
-        const int64_t r_end = min(r_begin + a.chunk_rows, a.seg.rows[s + 1]);
+    while (row < cta_end) {
+        while (s < S - 1 && a.seg.rows[s + 1] <= row) ++s;  // skip empty segments
+        const int64_t r_end = min(a.seg.rows[s + 1], cta_end);
+        const int64_t r_begin = row;
         const uint32_t active = a.seg.mask_a[s];
         int cls[NA];
         {
@@ -67,20 +73,21 @@ __global__ void __launch_bounds__(512) proto_accum_kernel(const __grid_constant_
             acc[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             n_lab[i][0] = 0; n_lab[i][1] = 0;
         }
+        float4 fa[kProtoUnroll], fb[kProtoUnroll];
+        float ya[kProtoUnroll][NA], yb[kProtoUnroll][NA];
 
-        for (int64_t r0 = r_begin; r0 < r_end; r0 += kProtoUnroll) {
-            float4 f[kProtoUnroll];
-            float y[kProtoUnroll][NA];
+        auto load = [&](int64_t r0, float4* f, float (*y)[NA]) {
 #pragma unroll
             for (int u = 0; u < kProtoUnroll; ++u) {
-                const int64_t row = r0 + u;
-                const bool ok = row < r_end;
-                f[u] = (ok && col_ok) ? ld_stream_f4(a.feat + row * a.ld_feat + col)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int64_t r = r0 + u;
+                const bool ok = r < r_end;
+                f[u] = (ok && col_ok) ? ld_stream_f4(a.feat + r * a.ld_feat + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < NA; ++i)
-                    y[u][i] = (ok && cls[i] >= 0) ? __ldg(a.labels + row * a.C + cls[i]) : -1.f;
+                    y[u][i] = (ok && cls[i] >= 0) ? __ldg(a.labels + r * a.C + cls[i]) : -1.f;
             }
+        };
+        auto consume = [&](const float4* f, const float (*y)[NA]) {
 #pragma unroll
             for (int u = 0; u < kProtoUnroll; ++u) {
 #pragma unroll
@@ -95,106 +102,160 @@ __global__ void __launch_bounds__(512) proto_accum_kernel(const __grid_constant_
                     }
                 }
             }
+        };
+        load(r_begin, fa, ya);
+        for (int64_t r0 = r_begin; r0 < r_end; r0 += 2 * kProtoUnroll) {
+            load(r0 + kProtoUnroll, fb, yb);
+            consume(fa, ya);
+            load(r0 + 2 * kProtoUnroll, fa, ya);
+            consume(fb, yb);
         }
+
+        const int64_t slot = (int64_t)blockIdx.x + s;
         if (col_ok) {
 #pragma unroll
             for (int i = 0; i < NA; ++i) {
-                float* dst = a.partial + ((item * NA + i) * 2) * (int64_t)a.D + col;
+                float* dst = a.partial + ((slot * NA + i) * 2) * (int64_t)a.D + col;
                 *reinterpret_cast<float4*>(dst) = acc[i][0];
                 *reinterpret_cast<float4*>(dst + a.D) = acc[i][1];
             }
         }
         if (blockIdx.y == 0) {
-            if (a.count_labels && threadIdx.x == 0) {
+            int32_t* pc = a.pcount + slot * kProtoCountStride;
+            if (threadIdx.x == 0) {
 #pragma unroll
-                for (int i = 0; i < NA; ++i)
-                    if (cls[i] >= 0) {
-                        if (n_lab[i][0]) atomicAdd(a.cnt + (int64_t)s * 2 * a.C + 2 * cls[i], n_lab[i][0]);
-                        if (n_lab[i][1]) atomicAdd(a.cnt + (int64_t)s * 2 * a.C + 2 * cls[i] + 1, n_lab[i][1]);
-                    }
+                for (int i = 0; i < NA; ++i) { pc[2 * i] = n_lab[i][0]; pc[2 * i + 1] = n_lab[i][1]; }
             }
             // confident-prediction counts (:995-996, :1239): #{p < L or p > U}
-            const uint32_t tmask = a.seg.mask_b[s];
-            if (a.logits != nullptr && a.tcnt != nullptr && tmask != 0u) {
+            if (a.do_t) {
+                const uint32_t tmask = a.seg.mask_b[s];
                 __syncthreads();
                 if (threadIdx.x < FMLP_MAX_CLASSES) s_t[threadIdx.x] = 0;
                 __syncthreads();
-                const int64_t n_el = (r_end - r_begin) * a.C;
-                const float* z = a.logits + r_begin * a.C;
-                for (int64_t e = threadIdx.x; e < n_el; e += blockDim.x) {
-                    const int c = (int)(e % a.C);
-                    if ((tmask >> c) & 1u) {
-                        const float v = z[e];
-                        const float p = a.logits_are_probs ? v : sigmoid_ref(v);
-                        if (p < a.L || p > a.U) atomicAdd(&s_t[c], 1);
+                if (a.logits != nullptr && tmask != 0u) {
+                    const int64_t n_el = (r_end - r_begin) * a.C;
+                    const float* z = a.logits + r_begin * a.C;
+                    for (int64_t e = threadIdx.x; e < n_el; e += blockDim.x) {
+                        const int c = (int)(e % a.C);
+                        if ((tmask >> c) & 1u) {
+                            const float v = z[e];
+                            const float p = a.logits_are_probs ? v : sigmoid_ref(v);
+                            if (p < a.L || p > a.U) atomicAdd(&s_t[c], 1);
+                        }
                     }
                 }
                 __syncthreads();
-                if (threadIdx.x < a.C && s_t[threadIdx.x] != 0)
-                    atomicAdd(a.tcnt + (int64_t)s * a.C + threadIdx.x, s_t[threadIdx.x]);
+                if (threadIdx.x < a.C) pc[2 * kProtoMaxActive + threadIdx.x] = s_t[threadIdx.x];
             }
         }
+        row = r_end;
+        if (row < cta_end) ++s;
     }
 }
 
 struct ProtoFinArgs {
     const float* partial;
-    const int32_t* cnt;  // [S][2C]
+    const int32_t* pcount;
     float* proto;        // [S][2C][D]
-    int64_t item_base[FMLP_MAX_SEGMENTS + 1];
+    int32_t* cnt;        // [S][2C]
+    int32_t* tcnt;       // [S][C] or null
+    int64_t rows_per_cta;
     SegTable seg;        // mask_a = active classes of THIS pass; mask_b = all active classes
-    int D, C, NA, guard_empty, first_pass;
+    int D, C, NA, guard_empty, first_pass, has_t;
 };
 
-// grid = (S * 2C, ceil(D / 256)).  Row 2c+y of segment s: sum the chunk partials in chunk
-// order, divide by the row count (tensor / python int -> fp32 divide, :997-999,1241-1248).
+// grid = (S * 2C, ceil(D / 256)).  Row 2c+y of segment s: add the slot partials in CTA order,
+// divide by the row count (tensor / python int -> fp32 divide, :997-999,1241-1248).
 __global__ void __launch_bounds__(256) proto_finalize_kernel(const __grid_constant__ ProtoFinArgs a) {
     const int s = blockIdx.x / (2 * a.C);
     const int row = blockIdx.x - s * 2 * a.C;
     const int c = row >> 1, y = row & 1;
     const int d = blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t seg_lo = a.seg.rows[s], seg_hi = a.seg.rows[s + 1];
+    const bool nonempty = seg_hi > seg_lo;
+    const int64_t b0 = nonempty ? seg_lo / a.rows_per_cta : 0;
+    const int64_t b1 = nonempty ? (seg_hi - 1) / a.rows_per_cta : -1;
+    const uint32_t pass_active = a.seg.mask_a[s];
+    const bool mine = (pass_active >> c) & 1u;
+    const bool active_any = (a.seg.mask_b[s] >> c) & 1u;
+
+    // t counts: rows 0..C-1 of the first pass double as "class row" (one warp adds the slots)
+    if (a.first_pass && a.tcnt != nullptr && blockIdx.y == 0 && row < a.C && threadIdx.x < 32) {
+        int t = 0;
+        if (a.has_t)
+            for (int64_t b = b0 + threadIdx.x; b <= b1; b += 32)
+                t += a.pcount[(b + s) * kProtoCountStride + 2 * kProtoMaxActive + row];
+        t = warp_sum_i(t);
+        if (threadIdx.x == 0) a.tcnt[(int64_t)s * a.C + row] = t;
+    }
+    const int slot_i = __popc(pass_active & ((1u << c) - 1u));  // position among this pass's classes
+    // row count: the slots are independent loads -> spread them over the CTA, then add
+    __shared__ int s_n[8];
+    int n = 0;
+    if (mine)
+        for (int64_t b = b0 + threadIdx.x; b <= b1; b += blockDim.x) n += a.pcount[(b + s) * kProtoCountStride + 2 * slot_i + y];
+    n = warp_sum_i(n);
+    if ((threadIdx.x & 31) == 0) s_n[threadIdx.x >> 5] = n;
+    __syncthreads();
+    n = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n += s_n[w];
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+        if (mine) a.cnt[(int64_t)s * 2 * a.C + row] = n;
+        else if (a.first_pass && !active_any) a.cnt[(int64_t)s * 2 * a.C + row] = 0;
+    }
     if (d >= a.D) return;
     float* out = a.proto + ((int64_t)s * 2 * a.C + row) * a.D + d;
-    const uint32_t pass_active = a.seg.mask_a[s];
-    if (!((pass_active >> c) & 1u)) {
+    if (!mine) {
         // rows of classes that are not active on this client stay zero (proto = torch.zeros, :973)
-        if (a.first_pass && !((a.seg.mask_b[s] >> c) & 1u)) *out = 0.f;
+        if (a.first_pass && !active_any) *out = 0.f;
         return;
     }
-    const int slot = __popc(pass_active & ((1u << c) - 1u));  // position among this pass's classes
-    const int64_t i0 = a.item_base[s], i1 = a.item_base[s + 1];
+    // slot partials are added in CTA order (deterministic); loads are issued 8 at a time so the
+    // L2 round trips overlap instead of forming one dependent chain
     float acc = 0.f;
-    for (int64_t it = i0; it < i1; ++it)
-        acc += a.partial[((it * a.NA + slot) * 2 + y) * (int64_t)a.D + d];
-    const int n = a.cnt[(int64_t)s * 2 * a.C + row];
+    const float* p0 = a.partial + ((int64_t)slot_i * 2 + y) * (int64_t)a.D + d;
+    const int64_t slot_stride = (int64_t)a.NA * 2 * a.D;
+    int64_t b = b0;
+    for (; b + 8 <= b1 + 1; b += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p0[(b + u + s) * slot_stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; b <= b1; ++b) acc += p0[(b + s) * slot_stride];
     if (n == 0 && a.guard_empty) *out = acc;  // == 0
     else *out = __fdiv_rn(acc, (float)n);
 }
 
-__global__ void zero_i32_kernel(int32_t* p, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
+template <int NA>
+static int proto_ctas_per_sm(int threads) {
+    static int cached_threads = 0, cached = 0;
+    if (cached_threads != threads) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, proto_accum_kernel<NA>, threads, 0) != cudaSuccess) b = 1;
+        cached = b < 1 ? 1 : (b > kProtoMaxCtasPerSm ? kProtoMaxCtasPerSm : b);
+        cached_threads = threads;
+    }
+    return cached;
 }
 
 }  // namespace fmlp
 
 using namespace fmlp;
 
-static int64_t proto_items(const int64_t* seg_rows, int S, int chunk, int64_t* item_base) {
-    int64_t n = 0;
-    for (int s = 0; s < S; ++s) {
-        if (item_base) item_base[s] = n;
-        n += (seg_rows[s + 1] - seg_rows[s] + chunk - 1) / chunk;
-    }
-    if (item_base) for (int s = S; s <= FMLP_MAX_SEGMENTS; ++s) item_base[s] = n;
-    return n;
+static size_t proto_slot_bytes(int D) {
+    return (size_t)kProtoMaxActive * 2 * (size_t)D * sizeof(float);
 }
 
 extern "C" size_t fmlp_proto_ws_bytes(int64_t n_total, int D, int C, int S) {
-    (void)C;
-    if (n_total < 0 || D < 1 || S < 1) return 0;
-    const int chunk = proto_chunk_rows(n_total);
-    const int64_t items = n_total / chunk + S;  // upper bound on sum of ceil(N_s / chunk)
-    return (size_t)items * kProtoMaxActive * 2 * (size_t)D * sizeof(float);
+    (void)C; (void)n_total;
+    if (D < 1 || S < 1) return 0;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const size_t slots = (size_t)sms * kProtoMaxCtasPerSm + (size_t)S;
+    return slots * (proto_slot_bytes(D) + kProtoCountStride * sizeof(int32_t));
 }
 
 extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, const float* labels,
@@ -207,33 +268,27 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
         return FMLP_ERR_BAD_ARG;
     if (logits && !tcnt) return FMLP_ERR_BAD_ARG;
     if ((D & 3) || (ld_feat & 3) || ld_feat < D || !aligned16(feat) || !aligned16(ws)) return FMLP_ERR_UNSUPPORTED;
+    if (S < 1 || S > FMLP_MAX_SEGMENTS || !seg_rows) return FMLP_ERR_BAD_ARG;
     const uint32_t cmask = C < 32 ? ((1u << C) - 1u) : 0xffffffffu;
     cudaStream_t st = (cudaStream_t)stream;
+    const int sms = sm_count();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    const size_t max_slots = (size_t)sms * kProtoMaxCtasPerSm + (size_t)S;
+    if (ws_bytes < max_slots * (proto_slot_bytes(D) + kProtoCountStride * sizeof(int32_t))) return FMLP_ERR_WORKSPACE;
 
-    ProtoArgs a;
     uint32_t act_all[FMLP_MAX_SEGMENTS], act_left[FMLP_MAX_SEGMENTS], tc[FMLP_MAX_SEGMENTS];
-    if (S < 1 || S > FMLP_MAX_SEGMENTS || !seg_rows) return FMLP_ERR_BAD_ARG;
     for (int s = 0; s < S; ++s) {
         act_all[s] = seg_active[s] & cmask;
         act_left[s] = act_all[s];
         tc[s] = (seg_tcount ? seg_tcount[s] : 0u) & cmask;
     }
     const int64_t n_total = seg_rows[S];
-    const int chunk = proto_chunk_rows(n_total);
-    const int64_t n_items = proto_items(seg_rows, S, chunk, a.item_base);
-    if (ws_bytes < (size_t)n_items * kProtoMaxActive * 2 * (size_t)D * sizeof(float)) return FMLP_ERR_WORKSPACE;
 
-    // counters are accumulated with integer atomics -> clear them first
-    const int64_t n_cnt = (int64_t)S * 2 * C;
-    zero_i32_kernel<<<1, 256, 0, st>>>(cnt, n_cnt);
-    if (tcnt) zero_i32_kernel<<<1, 256, 0, st>>>(tcnt, (int64_t)S * C);
+    ProtoArgs a;
+    a.feat = feat; a.labels = labels; a.logits = logits; a.partial = (float*)ws;
+    a.pcount = (int32_t*)((char*)ws + max_slots * proto_slot_bytes(D));
+    a.ld_feat = ld_feat; a.L = L; a.U = U; a.D = D; a.C = C; a.logits_are_probs = logits_are_probs;
 
-    a.feat = feat; a.labels = labels; a.logits = logits; a.partial = (float*)ws; a.cnt = cnt; a.tcnt = tcnt;
-    a.ld_feat = ld_feat; a.L = L; a.U = U; a.D = D; a.C = C; a.chunk_rows = chunk;
-    a.logits_are_probs = logits_are_probs; a.count_labels = 1;
-
-    const int sms = sm_count();
-    if (sms <= 0) return (int)cudaErrorInvalidDevice;
     const int nvec = D / 4;
     int threads = ((nvec + 31) / 32) * 32;
     if (threads > 512) threads = 512;
@@ -252,14 +307,23 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
             act_left[s] &= ~take;
             if (n > na_max) na_max = n;
         }
-        if (na_max == 0 && !first) break;
         int rc = fill_seg_table(a.seg, S, seg_rows, pass, first ? tc : nullptr);
         if (rc != FMLP_OK) return rc;
+        a.do_t = (first && logits != nullptr && tcnt != nullptr) ? 1 : 0;
         const int NA = na_max <= 1 ? 1 : (na_max == 2 ? 2 : 4);
-        if (n_items > 0) {
-            int64_t gx = n_items;
-            const int64_t cap = (int64_t)sms * 8;
-            if (gx > cap) gx = cap;
+        // one balanced wave: as many CTAs as can be co-resident, each with a contiguous row range
+        int per_sm = NA == 1 ? proto_ctas_per_sm<1>(threads) : (NA == 2 ? proto_ctas_per_sm<2>(threads) : proto_ctas_per_sm<4>(threads));
+        int64_t gx = (int64_t)sms * per_sm / gy;
+        if (gx < 1) gx = 1;
+        const int64_t min_rows = 2 * kProtoUnroll;
+        if (gx > (n_total + min_rows - 1) / min_rows) gx = (n_total + min_rows - 1) / min_rows;
+        if (gx < 1) gx = 1;
+        int64_t rpc = (n_total + gx - 1) / gx;
+        rpc = (rpc + kProtoUnroll - 1) / kProtoUnroll * kProtoUnroll;
+        if (rpc < kProtoUnroll) rpc = kProtoUnroll;
+        a.rows_per_cta = rpc;
+        if (n_total > 0) {
+            gx = (n_total + rpc - 1) / rpc;
             dim3 grid((unsigned)gx, (unsigned)gy);
             if (NA == 1) proto_accum_kernel<1><<<grid, threads, 0, st>>>(a);
             else if (NA == 2) proto_accum_kernel<2><<<grid, threads, 0, st>>>(a);
@@ -268,11 +332,11 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
             if (rc != FMLP_OK) return rc;
         }
         ProtoFinArgs f;
-        f.partial = (const float*)ws; f.cnt = cnt; f.proto = proto;
-        for (int s = 0; s <= FMLP_MAX_SEGMENTS; ++s) f.item_base[s] = a.item_base[s];
+        f.partial = a.partial; f.pcount = a.pcount; f.proto = proto; f.cnt = cnt; f.tcnt = tcnt;
+        f.rows_per_cta = rpc;
         rc = fill_seg_table(f.seg, S, seg_rows, pass, act_all);
         if (rc != FMLP_OK) return rc;
-        f.D = D; f.C = C; f.NA = NA; f.guard_empty = guard_empty; f.first_pass = first ? 1 : 0;
+        f.D = D; f.C = C; f.NA = NA; f.guard_empty = guard_empty; f.first_pass = first ? 1 : 0; f.has_t = a.do_t;
         dim3 fgrid((unsigned)(S * 2 * C), (unsigned)((D + 255) / 256));
         proto_finalize_kernel<<<fgrid, 256, 0, st>>>(f);
         rc = launch_status();

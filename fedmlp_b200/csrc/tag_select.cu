@@ -12,6 +12,8 @@
 // tie behaviour of Python's stable sort in both max_m_indices (reverse=True keeps the original
 // order of equal elements) and min_n_indices.  All comps of an item are distinct, so the
 // selection "comp >= T" has exactly m (resp. k) members.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fmlp {
@@ -67,7 +69,13 @@ __device__ __forceinline__ unsigned long long make_comp(float s, uint32_t local_
 // side: 0 clean (sim >= 0), 1 noise (sim < 0), -1 neither (NaN) — np.where(sim >= 0) / (sim < 0)
 __device__ __forceinline__ int side_of(float s) { return s >= 0.f ? 0 : (s < 0.f ? 1 : -1); }
 
+// IPT > 0: every thread keeps its IPT candidate keys in registers for all passes (segments of up
+// to IPT * kSelThreads rows); IPT == 0: keys are re-read from global memory in every pass.
+// key = comp | side << 63.
+template <int IPT>
 __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid_constant__ SelArgs a) {
+    constexpr bool CACHED = IPT > 0;
+    constexpr int NK = CACHED ? IPT : 1;
     __shared__ int s_hist[2][kSelBins];  // reused as the rank staging tile (2048 x u64)
     __shared__ int s_warp[kSelThreads / 32 + 1];
     __shared__ int s_found[3];           // bin, remaining-in-bin, bin count
@@ -84,6 +92,45 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
     const uint32_t n = (uint32_t)(a.seg.rows[s + 1] - r0);
     const float* sim = a.sim + (int64_t)c * a.ld_sim + r0;
     uint8_t* tag = a.tag + (int64_t)c * a.ld_tag + r0;
+    constexpr unsigned long long kSideBit = 1ull << 63;
+
+    // ---- candidate keys ------------------------------------------------------------------
+    unsigned long long key[NK];
+    uint32_t valid = 0;
+    if (CACHED) {
+        float v[NK];
+        uint8_t tg[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const uint32_t i = (uint32_t)k * kSelThreads + threadIdx.x;
+            const bool in = i < n;
+            tg[k] = in ? tag[i] : (uint8_t)1;
+            v[k] = in ? sim[i] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const uint32_t i = (uint32_t)k * kSelThreads + threadIdx.x;
+            const int sd = side_of(v[k]);
+            key[k] = make_comp(v[k], i) | (sd == 1 ? kSideBit : 0ull);
+            if (tg[k] == 0 && sd >= 0) valid |= 1u << k;
+        }
+    }
+    // visit every candidate key of this thread
+    auto for_each = [&](auto&& fn) {
+        if (CACHED) {
+#pragma unroll
+            for (int k = 0; k < NK; ++k)
+                if ((valid >> k) & 1u) fn(key[k]);
+        } else {
+            for (uint32_t i = threadIdx.x; i < n; i += kSelThreads) {
+                if (tag[i] != 0) continue;
+                const float v = sim[i];
+                const int sd = side_of(v);
+                if (sd < 0) continue;
+                fn(make_comp(v, i) | (sd == 1 ? kSideBit : 0ull));
+            }
+        }
+    };
 
     unsigned long long prefix[2] = {0ull, 0ull};
     unsigned long long thresh[2] = {~0ull, ~0ull};  // comp >= thresh selects; ~0 selects nothing
@@ -99,15 +146,15 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
         for (int i = threadIdx.x; i < 2 * kSelBins; i += kSelThreads) (&s_hist[0][0])[i] = 0;
         __syncthreads();
         const unsigned long long dmask = (1ull << width) - 1ull;
-        for (uint32_t i = threadIdx.x; i < n; i += kSelThreads) {
-            if (tag[i] != 0) continue;
-            const float v = sim[i];
-            const int sd = side_of(v);
-            if (sd < 0 || done[sd]) continue;
-            const unsigned long long comp = make_comp(v, i);
-            if (pass == 0 || (comp >> (shift + width)) == prefix[sd])
+        const unsigned long long pre0 = prefix[0], pre1 = prefix[1];
+        const bool d0 = done[0], d1 = done[1];
+        for_each([&](unsigned long long k) {
+            const int sd = (int)(k >> 63);
+            const unsigned long long comp = k & ~kSideBit;
+            if (sd ? d1 : d0) return;
+            if (pass == 0 || (comp >> (shift + width)) == (sd ? pre1 : pre0))
                 atomicAdd(&s_hist[sd][(int)((comp >> shift) & dmask)], 1);
-        }
+        });
         __syncthreads();
 #pragma unroll
         for (int sd = 0; sd < 2; ++sd) {
@@ -158,17 +205,17 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
     // ---- compaction: mark the tag state and collect the selected comps -------------------
     if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += kSelThreads) {
-        if (tag[i] != 0) continue;
-        const float v = sim[i];
-        const int sd = side_of(v);
-        if (sd < 0) continue;
-        const unsigned long long comp = make_comp(v, i);
-        if (comp >= thresh[sd]) {
-            const int slot = atomicAdd(&s_count[sd], 1);
-            if (slot < a.cap) a.cand[((int64_t)item * 2 + sd) * a.cap + slot] = comp;
-            tag[i] = (uint8_t)(1 + sd);
-        }
+    {
+        const unsigned long long t0 = thresh[0], t1 = thresh[1];
+        for_each([&](unsigned long long k) {
+            const int sd = (int)(k >> 63);
+            const unsigned long long comp = k & ~kSideBit;
+            if (comp >= (sd ? t1 : t0)) {
+                const int slot = atomicAdd(&s_count[sd], 1);
+                if (slot < a.cap) a.cand[((int64_t)item * 2 + sd) * a.cap + slot] = comp;
+                tag[0xFFFFFFFFu - (uint32_t)(comp & 0xFFFFFFFFull)] = (uint8_t)(1 + sd);
+            }
+        });
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -179,7 +226,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
     unsigned long long* tile = reinterpret_cast<unsigned long long*>(&s_hist[0][0]);  // 2048 entries
     constexpr int kTile = 2048;
     for (int sd = 0; sd < 2; ++sd) {
-        const int cnt = min((int64_t)s_count[sd], a.cap);
+        const int cnt = (int)min((int64_t)s_count[sd], a.cap);
         const unsigned long long* cand = a.cand + ((int64_t)item * 2 + sd) * a.cap;
         int32_t* out = a.sel + ((int64_t)item * 2 + sd) * a.cap;
         for (int e0 = 0; e0 < cnt; e0 += kSelThreads) {
@@ -259,7 +306,14 @@ extern "C" int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, i
     a.sim = sim; a.tag = tag; a.counts = counts; a.sel = sel; a.cand = (unsigned long long*)ws;
     a.ld_sim = ld_sim; a.ld_tag = ld_tag; a.cap = cap; a.clean_frac = clean_frac; a.noise_frac = noise_frac;
     a.C = C;
-    tag_select_kernel<<<(unsigned)(S * C), kSelThreads, 0, (cudaStream_t)stream>>>(a);
+    int64_t max_rows = 0;
+    for (int s = 0; s < S; ++s) max_rows = std::max<int64_t>(max_rows, seg_rows[s + 1] - seg_rows[s]);
+    const unsigned grid = (unsigned)(S * C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_rows <= 8 * kSelThreads) tag_select_kernel<8><<<grid, kSelThreads, 0, st>>>(a);
+    else if (max_rows <= 16 * kSelThreads) tag_select_kernel<16><<<grid, kSelThreads, 0, st>>>(a);
+    else if (max_rows <= 32 * kSelThreads) tag_select_kernel<32><<<grid, kSelThreads, 0, st>>>(a);
+    else tag_select_kernel<0><<<grid, kSelThreads, 0, st>>>(a);
     return launch_status();
 }
 

@@ -7,13 +7,22 @@
 //
 // Mapping: the prototype vectors of the classes to score live in shared memory for the whole
 // (persistent) CTA; each warp owns a tile of R consecutive rows and walks D in 128-column
-// steps (one coalesced 512-B request per row per step, software-pipelined one step ahead).
-// A prototype float4 read from smem feeds 4*R FMAs, which keeps the smem pipe below the FMA
-// pipe; per-row partials are combined with warp shuffles.  Work per byte is (2M+1)/4 FMA, so
-// for C <= 8 the kernel is HBM-bound; FMLP_SIM_FOLDED halves the FMAs for larger C.
+// chunks (one coalesced 512-B request per row per chunk, ping-pong buffered one chunk ahead).
+// The first version of this kernel was ISSUE-bound (ncu r01: 981 warp-instructions per row,
+// only 38 % of them FMAs), so this one is built to minimise instructions:
+//   * packed fp32 FMAs (fma.rn.f32x2 -> SASS FFMA2): features and prototypes are loaded as
+//     64-bit pairs, every accumulator is an (even, odd) pair -> half the FMA instructions;
+//   * a prototype pair read from smem feeds R rows, the chunk loop is unrolled x2 so the
+//     ping-pong needs no register moves, D % 128 == 0 is a template flag (no column predicates);
+//   * the R*(NV+1) per-lane partials are combined with a transposed (recursive-halving) warp
+//     reduction: ~V shuffles instead of 5V, then ONE lane per (row, class) does the epilogue
+//     from a per-warp smem scratch instead of all 32 lanes doing all of them redundantly.
+// Work per byte is (2M+1)/4 FMA; FMLP_SIM_FOLDED halves that for large C.
 #include "common.cuh"
 
 namespace fmlp {
+
+using u64 = unsigned long long;
 
 struct SimArgs {
     const float* feat;
@@ -32,25 +41,80 @@ struct SimArgs {
 template <int NPAIR, bool FOLD>
 struct SimCfg {
     static constexpr int NV = FOLD ? NPAIR : 2 * NPAIR;
-    static constexpr int R = 4;
-    // > 16 accumulators per row need more than the 128 registers a 512-thread CTA allows.
-    static constexpr int THREADS = (NV > 16) ? 256 : 512;
+    static constexpr int R = (NV <= 16) ? 4 : 2;            // rows per warp tile
+#ifndef FMLP_SIM_THREADS_SMALL
+#define FMLP_SIM_THREADS_SMALL 384
+#endif
+    static constexpr int THREADS = (NV <= 10) ? FMLP_SIM_THREADS_SMALL : 256;  // register caps 168 (384 thr) / 255
+    static constexpr int V = R * (NV + 1);                  // values reduced per tile
+    static constexpr int SCRATCH = (V + 3) & ~3;
 };
 
-template <int NPAIR, bool FOLD>
+__device__ __forceinline__ void fma2(u64& acc, u64 a, u64 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float pair_sum(u64 v) {
+    float lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+// 128-bit streaming load returned as two packed fp32 pairs
+__device__ __forceinline__ void ldg_pairs(const float* p, u64& a, u64& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+__device__ __forceinline__ void lds_pairs(uint32_t saddr, u64& a, u64& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
+}
+
+// One stage of the transposed warp reduction: CUR values per lane -> ceil(CUR/2), lanes whose
+// MASK bit is set keep the upper half.
+template <int CUR, int MASK>
+__device__ __forceinline__ void reduce_stage(float* v, int lane) {
+    constexpr int HALF = (CUR + 1) / 2;
+    const bool up = (lane & MASK) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const float a = v[i];
+        const float b = (i + HALF < CUR) ? v[i + HALF] : 0.f;
+        const float send = up ? a : b;
+        const float keep = up ? b : a;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+}
+template <int V>
+struct Halving {
+    static constexpr int h0 = (V + 1) / 2, h1 = (h0 + 1) / 2, h2 = (h1 + 1) / 2, h3 = (h2 + 1) / 2,
+                         h4 = (h3 + 1) / 2;  // values per lane after the stages with mask 16, 8, 4, 2, 1
+    // original value index held in slot i of `lane` after all five stages, or -1 for padding
+    __device__ static int index_of(int i, int lane) {
+        int s = i;
+        if (s >= h4) return -1;
+        s += h4 * (lane & 1);         if (s >= h3) return -1;
+        s += h3 * ((lane >> 1) & 1);  if (s >= h2) return -1;
+        s += h2 * ((lane >> 2) & 1);  if (s >= h1) return -1;
+        s += h1 * ((lane >> 3) & 1);  if (s >= h0) return -1;
+        s += h0 * ((lane >> 4) & 1);  if (s >= V) return -1;
+        return s;
+    }
+};
+
+template <int NPAIR, bool FOLD, bool ALIGNED>
 __global__ void __launch_bounds__(SimCfg<NPAIR, FOLD>::THREADS, 1)
 tag_sim_kernel(const __grid_constant__ SimArgs a) {
     using Cfg = SimCfg<NPAIR, FOLD>;
     constexpr int NV = Cfg::NV;
     constexpr int R = Cfg::R;
+    constexpr int V = Cfg::V;
+    using H = Halving<V>;
     extern __shared__ __align__(16) float smem[];
-    float* sP = smem;                          // [NV][Dpad]
-    float* sNorm = smem + (size_t)NV * a.Dpad; // [2*NPAIR] prototype norms (pair order)
+    const int D = a.D, Dpad = a.Dpad;
+    float* sP = smem;                                // [NV][Dpad]
+    float* sNorm = smem + (size_t)NV * Dpad;         // [2*NPAIR] prototype norms (pair order), padded to 4
+    float* sScratch = sNorm + ((2 * NPAIR + 3) & ~3);  // [warps][SCRATCH]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int D = a.D, Dpad = a.Dpad;
 
     // ---- prologue: prototype norms, then stage the vectors ----------------------------
     // |P_j| = sqrt(sum p^2) (torch.norm), one warp per prototype row.
@@ -81,6 +145,14 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     }
     __syncthreads();
 
+    // where the values this lane ends up with after the transposed reduction belong
+    int out_idx[H::h4];
+#pragma unroll
+    for (int i = 0; i < H::h4; ++i) out_idx[i] = H::index_of(i, lane);
+    float* scratch = sScratch + warp * Cfg::SCRATCH;
+    const uint32_t sP_addr = (uint32_t)__cvta_generic_to_shared(sP) + lane * 16;
+    const int nchunks = Dpad >> 7;
+
     // ---- main loop: one tile of R rows per warp -----------------------------------------
     const int64_t n_tiles = (a.n_total + R - 1) / R;
     const int64_t tile_stride = (int64_t)gridDim.x * nwarps;
@@ -91,86 +163,99 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
         for (int r = 0; r < R; ++r) {
             int64_t row = row0 + r;
             if (row >= a.n_total) row = a.n_total - 1;  // clamp: result discarded below
-            fr[r] = a.feat + row * a.ld_feat;
+            fr[r] = a.feat + row * a.ld_feat + lane * 4;
         }
-        float acc[R][NV];
-        float nrm[R];
+        u64 acc[R][NV];
+        u64 nrm[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            nrm[r] = 0.f;
+            nrm[r] = 0ull;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) acc[r][j] = 0.f;
+            for (int j = 0; j < NV; ++j) acc[r][j] = 0ull;
         }
-        float4 f[R], fn[R];
-        int col = lane * 4;
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            f[r] = (col < D) ? ld_stream_f4(fr[r] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (; col < Dpad; col += 128) {
-            const int ncol = col + 128;
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                fn[r] = (ncol < D) ? ld_stream_f4(fr[r] + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const float4 p = *reinterpret_cast<const float4*>(sP + (size_t)j * Dpad + col);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc[r][j] = fmaf(f[r].x, p.x, acc[r][j]);
-                    acc[r][j] = fmaf(f[r].y, p.y, acc[r][j]);
-                    acc[r][j] = fmaf(f[r].z, p.z, acc[r][j]);
-                    acc[r][j] = fmaf(f[r].w, p.w, acc[r][j]);
-                }
-            }
+        u64 fa0[R], fa1[R], fb0[R], fb1[R];  // ping-pong chunk buffers (packed pairs)
+
+        auto load_chunk = [&](int c, u64* f0, u64* f1) {
+            const bool in = ALIGNED ? (c < nchunks) : (c * 128 + lane * 4 < D);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                nrm[r] = fmaf(f[r].x, f[r].x, nrm[r]);
-                nrm[r] = fmaf(f[r].y, f[r].y, nrm[r]);
-                nrm[r] = fmaf(f[r].z, f[r].z, nrm[r]);
-                nrm[r] = fmaf(f[r].w, f[r].w, nrm[r]);
-                f[r] = fn[r];
+                if (in) ldg_pairs(fr[r] + c * 128, f0[r], f1[r]);
+                else { f0[r] = 0ull; f1[r] = 0ull; }
             }
+        };
+        auto compute_chunk = [&](int c, const u64* f0, const u64* f1) {
+            const uint32_t base = sP_addr + (uint32_t)c * 512u;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                u64 p0, p1;
+                lds_pairs(base + (uint32_t)j * (uint32_t)Dpad * 4u, p0, p1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) { fma2(acc[r][j], f0[r], p0); fma2(acc[r][j], f1[r], p1); }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) { fma2(nrm[r], f0[r], f0[r]); fma2(nrm[r], f1[r], f1[r]); }
+        };
+
+        load_chunk(0, fa0, fa1);
+        for (int c = 0; c < nchunks; c += 2) {
+            load_chunk(c + 1, fb0, fb1);
+            compute_chunk(c, fa0, fa1);
+            load_chunk(c + 2, fa0, fa1);
+            if (c + 1 < nchunks) compute_chunk(c + 1, fb0, fb1);
         }
-        // ---- combine the 32 lane partials ---------------------------------------------
+
+        // ---- combine the 32 lane partials (transposed reduction) ------------------------
+        float v[V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            nrm[r] = warp_sum(nrm[r]);
 #pragma unroll
-            for (int j = 0; j < NV; ++j) acc[r][j] = warp_sum(acc[r][j]);
+            for (int j = 0; j < NV; ++j) v[r * (NV + 1) + j] = pair_sum(acc[r][j]);
+            v[r * (NV + 1) + NV] = pair_sum(nrm[r]);
         }
-        // ---- epilogue: reference op order (norm product, reciprocal, multiply, subtract)
+        reduce_stage<V, 16>(v, lane);
+        reduce_stage<H::h0, 8>(v, lane);
+        reduce_stage<H::h1, 4>(v, lane);
+        reduce_stage<H::h2, 2>(v, lane);
+        reduce_stage<H::h3, 1>(v, lane);
+        __syncwarp();  // previous tile's epilogue reads are done
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int i = 0; i < H::h4; ++i)
+            if (out_idx[i] >= 0) scratch[out_idx[i]] = v[i];
+        __syncwarp();
+
+        // ---- epilogue: one lane per (row, class); reference op order (norm product,
+        //      reciprocal, multiply, subtract)
+        for (int e = lane; e < R * NPAIR; e += 32) {
+            const int r = e / NPAIR, q = e - r * NPAIR;
             const int64_t row = row0 + r;
             if (row < a.n_total) {
+                const int c = a.cls[q];
                 const int s = find_segment(a.seg.rows, a.seg.S, row);
-                const uint32_t missing = a.seg.mask_a[s];
-                const float nf = sqrtf(nrm[r]);
-#pragma unroll
-                for (int q = 0; q < NPAIR; ++q) {
-                    const int c = a.cls[q];
-                    float v;
+                if ((a.seg.mask_a[s] >> c) & 1u) {
+                    const float* rv = scratch + r * (NV + 1);
+                    const float nf = sqrtf(rv[NV]);
+                    float out;
                     if (FOLD) {
-                        v = __fmul_rn(acc[r][q], __frcp_rn(nf));
+                        out = __fmul_rn(rv[q], __frcp_rn(nf));
                     } else {
-                        const float c0 = __fmul_rn(acc[r][2 * q], __frcp_rn(__fmul_rn(nf, sNorm[2 * q])));
-                        const float c1 = __fmul_rn(acc[r][2 * q + 1], __frcp_rn(__fmul_rn(nf, sNorm[2 * q + 1])));
-                        v = __fsub_rn(c0, c1);
+                        const float c0 = __fmul_rn(rv[2 * q], __frcp_rn(__fmul_rn(nf, sNorm[2 * q])));
+                        const float c1 = __fmul_rn(rv[2 * q + 1], __frcp_rn(__fmul_rn(nf, sNorm[2 * q + 1])));
+                        out = __fsub_rn(c0, c1);
                     }
-                    if (((missing >> c) & 1u) && lane == ((r * NPAIR + q) & 31))
-                        a.sim[(int64_t)c * a.ld_sim + row] = v;
+                    a.sim[(int64_t)c * a.ld_sim + row] = out;
                 }
             }
         }
     }
 }
 
-template <int NPAIR, bool FOLD>
-static int launch_sim(const SimArgs& a, cudaStream_t st) {
+template <int NPAIR, bool FOLD, bool ALIGNED>
+static int launch_sim_inst(const SimArgs& a, cudaStream_t st) {
     using Cfg = SimCfg<NPAIR, FOLD>;
-    const size_t smem = ((size_t)Cfg::NV * a.Dpad + 2 * NPAIR) * sizeof(float);
+    const int warps = Cfg::THREADS / 32;
+    const size_t smem = ((size_t)Cfg::NV * a.Dpad + ((2 * NPAIR + 3) & ~3) + (size_t)warps * Cfg::SCRATCH) * sizeof(float);
     if (smem > 227u * 1024u) return FMLP_ERR_UNSUPPORTED;
-    auto kern = tag_sim_kernel<NPAIR, FOLD>;
+    auto kern = tag_sim_kernel<NPAIR, FOLD, ALIGNED>;
     static size_t configured = 0;  // per template instance
     if (smem > 48u * 1024u && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -179,13 +264,17 @@ static int launch_sim(const SimArgs& a, cudaStream_t st) {
     }
     const int sms = sm_count();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
-    const int warps = Cfg::THREADS / 32;
     const int64_t n_tiles = (a.n_total + Cfg::R - 1) / Cfg::R;
     int64_t blocks = (n_tiles + warps - 1) / warps;
     if (blocks > sms) blocks = sms;  // persistent: one CTA per SM
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, Cfg::THREADS, smem, st>>>(a);
     return launch_status();
+}
+
+template <int NPAIR, bool FOLD>
+static int launch_sim(const SimArgs& a, cudaStream_t st) {
+    return (a.D % 128 == 0) ? launch_sim_inst<NPAIR, FOLD, true>(a, st) : launch_sim_inst<NPAIR, FOLD, false>(a, st);
 }
 
 template <bool FOLD>

@@ -7,25 +7,26 @@ once: their rows are stored back to back in [N_total, D] matrices ("segments"), 
 of the round is ONE launch over all of them:
 
     tag         fmlp_tag_sim_f32 + fmlp_tag_select + fmlp_mask_fill       (K3 / K3b / K3c)
-    loss        fmlp_loss_stage2_f32 per client over its N_k rows          (K4)
+    loss        fmlp_loss_stage2_seg_f32: every client's rows, own denominators (K4)
     prototypes  fmlp_proto_build_f32                                       (K2)
     FedAvg      fmlp_fedavg_flat_f32 over the clients' flat parameter buffers (K1)
 
 This module is host-side orchestration only; bench.py and the multi-GPU driver (dist.py) use it.
+Memory is planned once (`_Plan`): every output and workspace is a persistent device buffer and
+every host-side argument array is pre-built, so a round is seven C calls and no allocation.
 The CNN forward/backward (cuDNN) sits between these stages in real training and is not part of
 the hot path measured here.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 
 import torch
 
-from .fedavg import fedavg_flat_buffers
 from . import _cabi as cabi
-from .losses import launch_stage2
-from .prototypes import PrototypeResult, build_prototypes
-from .tagging import TagBatch
+from .prototypes import PrototypeResult
+from .tagging import SIM_MODES, TagBatch
 
 
 @dataclass
@@ -39,13 +40,49 @@ class RoundResult:
     events: dict = field(default_factory=dict)
 
 
+class _Plan:
+    """Static buffers + pre-built ctypes arguments for one (D, P) configuration."""
+
+    def __init__(self, shard: "ClientShard", D: int, P: int):
+        lib = cabi.lib()
+        dev, S, C, N = shard.device, shard.S, shard.C, shard.N
+        self.D, self.P = D, P
+        f32, i32 = torch.float32, torch.int32
+        max_rows = max(shard.sizes, default=0)
+        cap = max(1, int(math.floor(max(shard.clean_frac, shard.noise_frac, 0.0) * max_rows)) + 1)
+        self.cap = min(cap, max(max_rows, 1))
+        self.counts = torch.zeros(S, C, 4, dtype=i32, device=dev)
+        self.sel = torch.full((S, C, 2, self.cap), -1, dtype=i32, device=dev)
+        self.y = torch.empty(N, C, dtype=f32, device=dev)
+        self.distill = torch.empty(N, C, dtype=f32, device=dev)
+        self.sup = torch.empty(N, C, dtype=f32, device=dev)
+        self.losses = torch.empty(S, dtype=f32, device=dev)
+        self.dz = torch.empty(N, C, dtype=f32, device=dev)
+        self.proto = torch.empty(S, 2 * C, D, dtype=f32, device=dev)
+        self.cnt = torch.empty(S, 2 * C, dtype=i32, device=dev)
+        self.tcnt = torch.zeros(S, C, dtype=i32, device=dev)
+        self.glob = torch.empty(P, dtype=f32, device=dev)
+        with torch.cuda.device(dev):
+            self.ws_select = torch.empty(max(lib.fmlp_tag_select_ws_bytes(S, C, self.cap), 256), dtype=torch.uint8, device=dev)
+            self.ws_loss = torch.empty(max(lib.fmlp_loss_ws_bytes(N, C), 256), dtype=torch.uint8, device=dev)
+            self.ws_proto = torch.empty(max(lib.fmlp_proto_ws_bytes(N, D, C, S), 256), dtype=torch.uint8, device=dev)
+        self.rows = cabi.i64_array(shard.seg_rows)
+        self.active = cabi.u32_array([cabi.class_mask(a) for a in shard.active])
+        self.missing = cabi.u32_array([cabi.class_mask(m) for m in shard.missing])
+
+
 class ClientShard:
     """The clients of one rank: tagging state + the batched round hot path."""
+
+    # traindata_idx bookkeeping costs two small device copies per round; benchmarks switch it off
+    keep_history = True
 
     def __init__(self, sizes, n_classes, active_classes, device=None, clean_frac=0.005, noise_frac=0.01,
                  L=0.3, U=0.7, sim_mode="pair", dataset_idx=None):
         self.sizes = [int(n) for n in sizes]
         self.S = len(self.sizes)
+        if self.S > cabi.MAX_SEGMENTS:
+            raise ValueError(f"a ClientShard holds at most {cabi.MAX_SEGMENTS} clients; use several shards")
         self.C = int(n_classes)
         self.seg_rows = [0]
         for n in self.sizes:
@@ -54,41 +91,82 @@ class ClientShard:
         self.active = [list(a) for a in active_classes]
         self.missing = [[c for c in range(self.C) if c not in a] for a in self.active]
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.clean_frac, self.noise_frac, self.L, self.U = clean_frac, noise_frac, L, U
+        self.clean_frac, self.noise_frac, self.L, self.U = float(clean_frac), float(noise_frac), float(L), float(U)
         self.sim_mode = sim_mode
         self.tagger = TagBatch(self.seg_rows, self.C, self.active, self.missing, dataset_idx=dataset_idx,
                                device=self.device)
+        self._plan = None
+
+    def plan(self, D, P) -> _Plan:
+        if self._plan is None or self._plan.D != D or self._plan.P != P:
+            self._plan = _Plan(self, D, P)
+        return self._plan
 
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
-        client_flats: S flat parameter buffers [P]; weights: S client weights (dict_len)."""
+        client_flats: S flat parameter buffers [P]; weights: S client weights (dict_len).
+        All inputs are contiguous fp32 CUDA tensors on this shard's device.  The returned tensors
+        are the shard's persistent buffers (overwritten by the next round)."""
+        N, C, S = self.N, self.C, self.S
+        D = feat_tag.shape[1]
+        if (tuple(feat_tag.shape) != (N, D) or tuple(feat_proto.shape) != (N, D) or tuple(labels.shape) != (N, C)
+                or tuple(logits.shape) != (N, C) or tuple(proto_glob.shape) != (2 * C, D) or len(client_flats) != S):
+            raise ValueError("round_hot_path: inconsistent shapes")
+        for t in (feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto, *client_flats):
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("round_hot_path needs contiguous float32 CUDA tensors (no CPU fallback)")
+        P = client_flats[0].numel()
+        pl = self.plan(D, P)
+        lib = cabi.lib()
+        check = cabi.check
+        tg = self.tagger
+        glob = pl.glob if fedavg_out is None else fedavg_out
+        if divisor is None:
+            divisor = sum(weights)
         ev = {}
+        dev = self.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            st = stream.cuda_stream
 
-        def mark(name):
-            if timers is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(torch.cuda.current_stream(self.device))
-                ev[name] = e
+            def mark(name):
+                if timers is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(stream)
+                    ev[name] = e
 
-        mark("start")
-        self.tagger.similarity(feat_tag, proto_glob, self.sim_mode)
-        mark("sim")
-        counts, sel, cap = self.tagger.select(self.clean_frac, self.noise_frac)
-        y, distill, sup = self.tagger.fill(labels)
-        mark("select_fill")
-        losses = torch.empty(self.S, dtype=torch.float32, device=self.device)
-        dz = torch.empty_like(logits)
-        for s in range(self.S):
-            r0, r1 = self.seg_rows[s], self.seg_rows[s + 1]
-            launch_stage2(logits[r0:r1], logits_glob[r0:r1], y[r0:r1], distill[r0:r1], cabi.LOSS2_SUP,
-                          losses[s:s + 1], dz[r0:r1])
-        mark("loss")
-        protos = build_prototypes(feat_proto, labels, logits_proto, self.active, self.missing, self.L, self.U,
-                                  guard_empty=True, seg_rows=self.seg_rows)
-        mark("proto")
-        glob = fedavg_flat_buffers(client_flats, weights, out=fedavg_out, divide=divide, divisor=divisor)
-        mark("fedavg")
-        return RoundResult(counts, sel, losses, dz, protos, glob, ev)
+            mark("start")
+            check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
+                                       tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], st), "fmlp_tag_sim_f32")
+            mark("sim")
+            check(lib.fmlp_tag_select(tg.sim.data_ptr(), tg.sim.shape[1], tg.tag.data_ptr(), tg.tag.shape[1], C, S,
+                                      pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),
+                                      pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(), pl.ws_select.numel(), st),
+                  "fmlp_tag_select")
+            check(lib.fmlp_mask_fill(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], C, S, pl.rows, pl.active,
+                                     pl.missing, pl.y.data_ptr(), pl.distill.data_ptr(), pl.sup.data_ptr(), st),
+                  "fmlp_mask_fill")
+            mark("select_fill")
+            check(lib.fmlp_loss_stage2_seg_f32(logits.data_ptr(), logits_glob.data_ptr(), pl.y.data_ptr(),
+                                               pl.distill.data_ptr(), C, S, pl.rows, cabi.LOSS2_SUP,
+                                               pl.losses.data_ptr(), pl.dz.data_ptr(), pl.ws_loss.data_ptr(),
+                                               pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
+            mark("loss")
+            check(lib.fmlp_proto_build_f32(feat_proto.data_ptr(), D, D, labels.data_ptr(), logits_proto.data_ptr(), 0,
+                                           C, S, pl.rows, pl.active, pl.missing, self.L, self.U, 1,
+                                           pl.proto.data_ptr(), pl.cnt.data_ptr(), pl.tcnt.data_ptr(),
+                                           pl.ws_proto.data_ptr(), pl.ws_proto.numel(), st), "fmlp_proto_build_f32")
+            mark("proto")
+            flags = cabi.FEDAVG_DIVIDE if divide else 0
+            check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]), cabi.f32_array(weights),
+                                           S, P, float(divisor), flags, glob.data_ptr(), st), "fmlp_fedavg_flat_f32")
+            mark("fedavg")
+        if self.keep_history:
+            # keep the lazily materialised host lists of the tagger in sync with this round's picks
+            tg._history.append((pl.counts.clone(), pl.sel.clone(), pl.cap))
+        tg._lists = None
+        return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz,
+                           PrototypeResult(pl.proto, pl.cnt, pl.tcnt, list(self.seg_rows)), glob, ev)

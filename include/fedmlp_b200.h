@@ -206,6 +206,12 @@ int fmlp_loss_stage2_f32(const float* z, const float* zg, const float* y, const 
                          int64_t B, int C, int variant, float* loss, float* dz, void* ws,
                          size_t ws_bytes, fmlp_stream_t stream);
 
+/* Segmented form: S clients' rows stored back to back, each with its own denominator and its own
+ * scalar loss, in one launch.  loss: device float[S].                                          */
+int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const float* y, const float* distill,
+                             int C, int S, const int64_t* seg_rows, int variant, float* loss,
+                             float* dz, void* ws, size_t ws_bytes, fmlp_stream_t stream);
+
 /* dz[i] *= *scale_dev  (upstream gradient of the scalar loss, read from device memory). */
 int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream);
 

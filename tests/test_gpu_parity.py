@@ -420,6 +420,33 @@ def test_loss_stage2_vs_oracle(F, B, C, extreme, variant):
     np.testing.assert_allclose(z.grad.cpu().numpy(), 3.0 * rdz.numpy(), rtol=1e-5, atol=3e-6 * float(rdz.abs().max()))
 
 
+@pytest.mark.parametrize("variant", ["sup", "sup_dis"])
+def test_loss_stage2_segmented(F, variant):
+    """One launch over several clients == per-client oracle losses (own denominators)."""
+    from fedmlp_b200.losses import launch_stage2_seg, LOSS2_VARIANTS
+    C = 5
+    sizes = [700, 0, 33, 6875, 1, 2049]
+    seg_rows = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    N = seg_rows[-1]
+    zs, y = _rand_logits(N, C, 99, extreme=True)
+    g = torch.Generator().manual_seed(4)
+    distill = (torch.rand(N, C, generator=g) < 0.6).float()
+    distill[:, 1] = 0
+    loss = torch.empty(len(sizes), device=DEV)
+    dz = torch.empty(N, C, device=DEV)
+    launch_stage2_seg(zs[0].to(DEV), zs[1].to(DEV), y.to(DEV), distill.to(DEV), seg_rows, LOSS2_VARIANTS[variant], loss, dz)
+    loss, dz = loss.cpu(), dz.cpu()
+    for s, n in enumerate(sizes):
+        r0, r1 = seg_rows[s], seg_rows[s + 1]
+        if n == 0:
+            assert torch.isnan(loss[s])
+            continue
+        ref_loss, rdz = O.loss_and_grads(lambda z, zg, t, d: O.stage2_loss(z, zg, t, d, variant),
+                                         zs[0][r0:r1], zs[1][r0:r1], y[r0:r1], distill[r0:r1], n_grad=1)
+        assert abs(float(loss[s]) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+        np.testing.assert_allclose(dz[r0:r1].numpy(), rdz.numpy(), rtol=1e-5, atol=1e-6 * float(rdz.abs().max()))
+
+
 def test_losses_golden_flow(F):
     """Per-step losses and logit gradients recorded from the reference's own training loop."""
     flow = gu.load("flow.npz")

@@ -1,0 +1,56 @@
+"""Round-level parity: the batched multi-client hot path (ClientShard.round_hot_path) against the
+oracle run client by client, the way the reference's sequential loop (main.py:135) would."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fedmlp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_round_hot_path_matches_per_client_oracle(lib):
+    import fedmlp_b200 as F
+    from fedmlp_b200.round import ClientShard
+
+    C, D, P = 5, 256, 10007 + 1          # P multiple of 4
+    sizes = [700, 333, 1201, 64]
+    S = len(sizes)
+    active = [[s % C] for s in range(S)]
+    cf, nf = 0.03, 0.06
+    shard = ClientShard(sizes, C, active, device=DEV, clean_frac=cf, noise_frac=nf)
+    states = [O.TaggingState(list(range(n)), shard.missing[s]) for s, n in enumerate(sizes)]
+    g = torch.Generator().manual_seed(11)
+    flats = [torch.randn(P, generator=g) for _ in range(S)]
+    for rnd in range(2):
+        data = [O.synth_client(n, D, C, seed=100 * rnd + s) for s, n in enumerate(sizes)]
+        data2 = [O.synth_client(n, D, C, seed=100 * rnd + 50 + s) for s, n in enumerate(sizes)]
+        feat = torch.cat([d[0] for d in data]); labels = torch.cat([d[1] for d in data])
+        logits = torch.cat([d[2] for d in data])
+        feat2 = torch.cat([d[0] for d in data2]); logits2 = torch.cat([d[2] for d in data2])
+        zg = torch.randn(sum(sizes), C, generator=g) * 2
+        proto = O.synth_prototypes(feat, labels)
+        res = shard.round_hot_path(feat.to(DEV), proto.to(DEV), logits.to(DEV), zg.to(DEV), labels.to(DEV),
+                                   feat2.to(DEV), logits2.to(DEV), [f.to(DEV) for f in flats], sizes)
+        t = res.protos.t()
+        for s, n in enumerate(sizes):
+            r0, r1 = shard.seg_rows[s], shard.seg_rows[s + 1]
+            sims_ref, stats = states[s].step(feat[r0:r1], proto, cf, nf)
+            got = shard.tagger.traindata_idx(s)
+            for j in range(2 * len(shard.missing[s])):
+                assert got[j] == [float(v) for v in states[s].traindata_idx[j]]
+            tgt, dis = O.mask_fill(labels[r0:r1].numpy(), list(range(n)), active[s], shard.missing[s], states[s].traindata_idx)
+            ref_loss, rdz = O.loss_and_grads(lambda z, g_, y, d: O.stage2_loss(z, g_, y, d), logits[r0:r1], zg[r0:r1],
+                                             torch.from_numpy(tgt), torch.from_numpy(dis), n_grad=1)
+            assert abs(float(res.losses[s]) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+            np.testing.assert_allclose(res.dz[r0:r1].cpu().numpy(), rdz.numpy(), rtol=1e-5, atol=1e-6 * float(rdz.abs().max()))
+            ref_p, ref_n, ref_t = O.prototype_build(feat2[r0:r1], labels[r0:r1], logits2[r0:r1], active[s], shard.missing[s],
+                                                    0.3, 0.7, guard_empty=True)
+            np.testing.assert_allclose(res.protos.proto[s].cpu().numpy(), ref_p.numpy(), rtol=1e-5, atol=1e-5 * float(ref_p.abs().max()))
+            assert res.protos.cnt[s].cpu().tolist() == ref_n
+            np.testing.assert_allclose(t[s], ref_t, rtol=0, atol=1.5 / n)
+        ref_glob = O.fedavg([OrderedDict(w=f) for f in flats], sizes)["w"]
+        assert torch.equal(res.global_flat.cpu(), ref_glob)
