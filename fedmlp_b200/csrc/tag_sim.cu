@@ -17,6 +17,10 @@
 //   * the R*(NV+1) per-lane partials are combined with a transposed (recursive-halving) warp
 //     reduction: ~V shuffles instead of 5V, then ONE lane per (row, class) does the epilogue
 //     from a per-warp smem scratch instead of all 32 lanes doing all of them redundantly.
+//   * features travel global -> shared with cp.async (LDGSTS) into a private ring per warp, DEPTH
+//     batches ahead of the math: B200 HBM wants ~100 KB in flight per SM (tools/exp_readpattern.cu)
+//     and the register file cannot hold that next to R*(NV+1) accumulator pairs.  Every lane reads
+//     back exactly the 16 bytes it copied, so the ring needs no cross-lane synchronisation.
 // Work per byte is (2M+1)/4 FMA; FMLP_SIM_FOLDED halves that for large C.
 #include "common.cuh"
 
@@ -48,6 +52,8 @@ struct SimCfg {
     static constexpr int THREADS = (NV <= 10) ? FMLP_SIM_THREADS_SMALL : 256;  // register caps 168 (384 thr) / 255
     static constexpr int V = R * (NV + 1);                  // values reduced per tile
     static constexpr int SCRATCH = (V + 3) & ~3;
+    static constexpr int DEPTH = 4;                         // cp.async batches in flight per warp
+    static constexpr int RING = DEPTH * R * 128;            // floats per warp
 };
 
 __device__ __forceinline__ void fma2(u64& acc, u64 a, u64 b) {
@@ -65,6 +71,13 @@ __device__ __forceinline__ void ldg_pairs(const float* p, u64& a, u64& b) {
 __device__ __forceinline__ void lds_pairs(uint32_t saddr, u64& a, u64& b) {
     asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
 }
+// 16-byte async copy global -> shared, L2 only (.cg); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const float* g, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One stage of the transposed warp reduction: CUR values per lane -> ceil(CUR/2), lanes whose
 // MASK bit is set keep the upper half.
@@ -111,6 +124,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     float* sP = smem;                                // [NV][Dpad]
     float* sNorm = smem + (size_t)NV * Dpad;         // [2*NPAIR] prototype norms (pair order), padded to 4
     float* sScratch = sNorm + ((2 * NPAIR + 3) & ~3);  // [warps][SCRATCH]
+    float* sRing = sScratch + (size_t)(blockDim.x >> 5) * Cfg::SCRATCH;  // [warps][DEPTH][R][128]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -153,18 +167,37 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     const uint32_t sP_addr = (uint32_t)__cvta_generic_to_shared(sP) + lane * 16;
     const int nchunks = Dpad >> 7;
 
-    // ---- main loop: one tile of R rows per warp -----------------------------------------
+    // ---- main loop: one tile of R rows per warp, features through the cp.async ring --------
+    constexpr int DEPTH = Cfg::DEPTH;
     const int64_t n_tiles = (a.n_total + R - 1) / R;
     const int64_t tile_stride = (int64_t)gridDim.x * nwarps;
-    for (int64_t t = (int64_t)blockIdx.x * nwarps + warp; t < n_tiles; t += tile_stride) {
-        const int64_t row0 = t * R;
-        const float* fr[R];
+    const int64_t t_first = (int64_t)blockIdx.x * nwarps + warp;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sRing + (size_t)warp * Cfg::RING) + lane * 16;
+    // producer cursor: batch = (tile, chunk), runs DEPTH-1 batches ahead of the math
+    int64_t t_issue = t_first;
+    int c_issue = 0, slot_issue = 0;
+    auto issue = [&]() {
+        if (t_issue < n_tiles) {
+            const int col = c_issue * 128 + lane * 4;
+            const int bytes = (ALIGNED || col < D) ? 16 : 0;
+            const int64_t row0 = t_issue * R;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int64_t row = row0 + r;
-            if (row >= a.n_total) row = a.n_total - 1;  // clamp: result discarded below
-            fr[r] = a.feat + row * a.ld_feat + lane * 4;
+            for (int r = 0; r < R; ++r) {
+                int64_t row = row0 + r;
+                if (row >= a.n_total) row = a.n_total - 1;  // clamp: result discarded in the epilogue
+                cp_async16(ring_addr + (uint32_t)((slot_issue * R + r) * 512), a.feat + row * a.ld_feat + (bytes ? col : 0), bytes);
+            }
+            if (++c_issue == nchunks) { c_issue = 0; t_issue += tile_stride; }
         }
+        cp_async_commit();  // empty groups keep the wait_group arithmetic uniform
+        slot_issue = (slot_issue + 1 == DEPTH) ? 0 : slot_issue + 1;
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) issue();
+    int slot = 0;
+
+    for (int64_t t = t_first; t < n_tiles; t += tile_stride) {
+        const int64_t row0 = t * R;
         u64 acc[R][NV];
         u64 nrm[R];
 #pragma unroll
@@ -173,17 +206,13 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
 #pragma unroll
             for (int j = 0; j < NV; ++j) acc[r][j] = 0ull;
         }
-        u64 fa0[R], fa1[R], fb0[R], fb1[R];  // ping-pong chunk buffers (packed pairs)
-
-        auto load_chunk = [&](int c, u64* f0, u64* f1) {
-            const bool in = ALIGNED ? (c < nchunks) : (c * 128 + lane * 4 < D);
+        for (int c = 0; c < nchunks; ++c) {
+            issue();
+            cp_async_wait<DEPTH - 1>();  // the batch issued DEPTH-1 calls ago has landed
+            u64 f0[R], f1[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (in) ldg_pairs(fr[r] + c * 128, f0[r], f1[r]);
-                else { f0[r] = 0ull; f1[r] = 0ull; }
-            }
-        };
-        auto compute_chunk = [&](int c, const u64* f0, const u64* f1) {
+            for (int r = 0; r < R; ++r) lds_pairs(ring_addr + (uint32_t)((slot * R + r) * 512), f0[r], f1[r]);
+            slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
             const uint32_t base = sP_addr + (uint32_t)c * 512u;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -194,14 +223,6 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) { fma2(nrm[r], f0[r], f0[r]); fma2(nrm[r], f1[r], f1[r]); }
-        };
-
-        load_chunk(0, fa0, fa1);
-        for (int c = 0; c < nchunks; c += 2) {
-            load_chunk(c + 1, fb0, fb1);
-            compute_chunk(c, fa0, fa1);
-            load_chunk(c + 2, fa0, fa1);
-            if (c + 1 < nchunks) compute_chunk(c + 1, fb0, fb1);
         }
 
         // ---- combine the 32 lane partials (transposed reduction) ------------------------
@@ -253,7 +274,7 @@ template <int NPAIR, bool FOLD, bool ALIGNED>
 static int launch_sim_inst(const SimArgs& a, cudaStream_t st) {
     using Cfg = SimCfg<NPAIR, FOLD>;
     const int warps = Cfg::THREADS / 32;
-    const size_t smem = ((size_t)Cfg::NV * a.Dpad + ((2 * NPAIR + 3) & ~3) + (size_t)warps * Cfg::SCRATCH) * sizeof(float);
+    const size_t smem = ((size_t)Cfg::NV * a.Dpad + ((2 * NPAIR + 3) & ~3) + (size_t)warps * (Cfg::SCRATCH + Cfg::RING)) * sizeof(float);
     if (smem > 227u * 1024u) return FMLP_ERR_UNSUPPORTED;
     auto kern = tag_sim_kernel<NPAIR, FOLD, ALIGNED>;
     static size_t configured = 0;  // per template instance

@@ -1,0 +1,162 @@
+"""Multi-GPU FedMLP rounds: clients are sharded over the ranks, only aggregation crosses GPUs.
+
+The reference is single-process / single-GPU and simulates its clients sequentially
+(main.py:32,135); its "communication" is a Python list of state_dicts (main.py:130,196).  Here
+one process drives one GPU (torchrun), each rank owns a contiguous block of the clients and runs
+tag / loss / prototypes for them with NO collective.  The only exchange step per round is the
+server aggregation (main.py:218-234):
+
+    FedAvg        rank-local K_r-way weighted partial sum (fedavg.cu, weights pre-normalised by the
+                  global total) -> ONE all-reduce(sum) of the flat fp32 parameter buffer over
+                  NCCL / NVLink -> every rank holds the identical global model.  int64 BatchNorm
+                  counters are all-reduced as exact int64 weighted sums and divided afterwards
+                  (bit-identical to the reference); the fp32 parameters differ from the
+                  reference's client-sequential fold only by summation association (<= 1e-6 rel).
+    FedAvg_proto  per-class weighted means over the clients that annotate the class
+    FedAvg_tao    per-class weighted means of the difficulty statistics (float64)
+
+`local_reduce` is injectable so the distributed algebra can be exercised on CPU with the gloo
+backend in tests (the CUDA kernel is the default and the only product path).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi as cabi
+from .fedavg import FedAvg_proto, _is_integral, fedavg_flat_buffers
+from .flat import FlatStateDict, layout_of
+
+
+def shard_clients(n_clients: int, world: int, rank: int) -> range:
+    """Contiguous block of client ids owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_clients, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def _world(group):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def _cuda_local_reduce(bufs, weights, out):
+    """sum_i bufs[i] * weights[i] on the GPU (fmlp_fedavg_flat_f32 without the final divide)."""
+    return fedavg_flat_buffers(bufs, weights, out=out, divide=False)
+
+
+def global_weight_sum(local_weights, group=None, device=None) -> float:
+    """sum of dict_len over all ranks (float64 all-reduce of one scalar)."""
+    t = torch.tensor([float(sum(local_weights))], dtype=torch.float64, device=device or "cpu")
+    if _world(group) > 1:
+        dist.all_reduce(t, group=group)
+    return float(t.item())
+
+
+def fedavg_flat_distributed(local_bufs, local_weights, total_weight=None, out=None, group=None,
+                            local_reduce=None):
+    """Global weighted mean of every client's flat fp32 buffer; each rank passes only its own
+    clients.  Returns the [P] mean (identical on every rank).  total_weight: sum of all clients'
+    weights over all ranks (computed with one extra scalar all-reduce when omitted)."""
+    if len(local_bufs) == 0:
+        raise ValueError("every rank needs at least one client")
+    dev = local_bufs[0].device
+    if total_weight is None:
+        total_weight = global_weight_sum(local_weights, group, dev if dev.type == "cuda" else None)
+    w = [float(x) / float(total_weight) for x in local_weights]   # float64 division, rounded once to fp32 by the kernel ABI
+    reduce_fn = local_reduce or _cuda_local_reduce
+    if out is None:
+        out = torch.empty_like(local_bufs[0])
+    partial = reduce_fn(local_bufs, w, out)
+    if _world(group) > 1:
+        dist.all_reduce(partial, group=group)
+    return partial
+
+
+def FedAvg_distributed(w_local, dict_len_local, group=None, total_weight=None, local_reduce=None):
+    """Distributed drop-in for FedAvg(w, dict_len) (reference utils/FedAvg.py:7-14): every rank
+    passes the state_dicts and weights of ITS clients; all ranks get the same averaged dict
+    (same keys/order; int64 entries become float32 like the reference)."""
+    if len(w_local) == 0:
+        raise ValueError("every rank needs at least one client")
+    first = next(iter(w_local[0].values()))
+    dev = first.device
+    layout = layout_of(w_local[0])
+    flats = []
+    for sd in w_local:
+        if layout_of(sd) is not layout:
+            raise KeyError("FedAvg_distributed: clients have different state_dict layouts")
+        if isinstance(sd, FlatStateDict) and not getattr(sd, "ints_as_float", False):
+            flats.append(sd)
+        else:
+            flats.append(FlatStateDict.from_state_dict(sd, device=dev))   # pack once (copy)
+    if total_weight is None:
+        total_weight = global_weight_sum(dict_len_local, group, dev if dev.type == "cuda" else None)
+    out = FlatStateDict.empty(layout, dev, ints_as_float=True)
+    if layout.n_f32:
+        fedavg_flat_distributed([f.flat_f32 for f in flats], dict_len_local, total_weight,
+                                out=out.flat_f32[:layout.n_f32], group=group, local_reduce=local_reduce)
+    if layout.n_i64:
+        integral = all(_is_integral(x) for x in dict_len_local)
+        if integral:
+            acc = torch.zeros(layout.n_i64, dtype=torch.int64, device=dev)
+            for f, n in zip(flats, dict_len_local):
+                acc += f.flat_i64 * int(n)                      # exact int64, like w[k] * dict_len[i]
+            if _world(group) > 1:
+                dist.all_reduce(acc, group=group)
+            out.flat_f32[layout.n_f32:] = acc.to(torch.float32) / float(total_weight)
+        else:
+            acc = torch.zeros(layout.n_i64, dtype=torch.float32, device=dev)
+            for f, n in zip(flats, dict_len_local):
+                acc += f.flat_i64.to(torch.float32) * float(n)
+            if _world(group) > 1:
+                dist.all_reduce(acc, group=group)
+            out.flat_f32[layout.n_f32:] = acc / float(total_weight)
+    return out
+
+
+def FedAvg_proto_distributed(protos_local, weight_local, class_active_local, n_classes, group=None,
+                             local_proto_avg=None):
+    """Distributed FedAvg_proto (reference utils/FedAvg.py:72-93).  protos_local: this rank's
+    client prototypes [2C, D]; class_active_local[c] = LOCAL client positions annotating class c.
+    Each rank forms its local per-class weighted mean, scales it by its share of the class
+    weight and one all-reduce adds the shares.  Classes nobody annotates give NaN rows, like the
+    reference's 0/0."""
+    avg_fn = local_proto_avg or FedAvg_proto
+    local = avg_fn(protos_local, weight_local, class_active_local)          # [2C, D]; NaN rows where empty
+    dev = local.device
+    wc = torch.zeros(n_classes, dtype=torch.float64, device=dev)
+    for c, clients in enumerate(class_active_local):
+        wc[c] = float(sum(weight_local[i] for i in clients))
+    total = wc.clone()
+    if _world(group) > 1:
+        dist.all_reduce(total, group=group)
+    share = torch.where(total > 0, wc / total.clamp_min(1e-300), torch.zeros_like(wc)).to(torch.float32)
+    rows = share.repeat_interleave(2).unsqueeze(1)                          # [2C, 1]
+    contrib = torch.where(rows > 0, local * rows, torch.zeros_like(local))  # drop this rank's NaN rows
+    if _world(group) > 1:
+        dist.all_reduce(contrib, group=group)
+    nobody = (total == 0).repeat_interleave(2).unsqueeze(1)
+    return torch.where(nobody, torch.full_like(contrib, float("nan")), contrib)
+
+
+def FedAvg_tao_distributed(t_local, weight_local, class_client_local, n_classes, group=None):
+    """Distributed FedAvg_tao (reference utils/FedAvg.py:51-70, float64): class_client_local[c] =
+    LOCAL client positions for which class c is missing; a class nobody misses gets 1.0."""
+    num = np.zeros(n_classes, dtype=np.float64)
+    den = np.zeros(n_classes, dtype=np.float64)
+    for c, clients in enumerate(class_client_local):
+        for i in clients:
+            num[c] += t_local[i][c] * float(weight_local[i])
+            den[c] += float(weight_local[i])
+    packed = torch.from_numpy(np.concatenate([num, den]))
+    if _world(group) > 1:
+        backend = dist.get_backend(group)
+        if backend == "nccl":
+            packed = packed.cuda()
+        dist.all_reduce(packed, group=group)
+        packed = packed.cpu()
+    num, den = packed[:n_classes].numpy(), packed[n_classes:].numpy()
+    return np.where(den > 0, num / np.where(den > 0, den, 1.0), 1.0)

@@ -1,0 +1,94 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/fedmlp_b200.h
+declares (no compute calls without a GPU), argument validation returns the documented status
+codes, and the host-side plumbing (flat layouts, DenseNet121 shapes, no-fallback errors)."""
+import ctypes
+import re
+from collections import OrderedDict
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from fedmlp_b200 import _cabi
+    header = (ROOT / "include" / "fedmlp_b200.h").read_text()
+    declared = set(re.findall(r"\b(fmlp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"fmlp_status", "fmlp_stream_t"}
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(str(_cabi.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_cabi.SIGNATURES) == declared
+    assert lib.fmlp_abi_version() == _cabi.ABI_VERSION
+    assert b"workspace" in lib.fmlp_status_string(-3)
+
+
+def test_argument_validation_without_gpu(lib):
+    from fedmlp_b200 import _cabi as c
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.fmlp_fedavg_flat_f32(None, None, 1, 10, 1.0, 1, None, None) == -1
+    assert lib.fmlp_fedavg_flat_f32(c.ptr_array([16]), c.f32_array([1.0]), 65, 10, 1.0, 1, 16, None) == -1
+    assert lib.fmlp_tag_sim_f32(None, 4, 4, None, 5, 1, None, None, None, 0, 0, None) == -1
+    assert lib.fmlp_loss_stage2_f32(None, None, None, None, 1, 5, 0, None, None, None, 0, None) == -1
+    # misaligned / unsupported shapes
+    rows = c.i64_array([0, 8])
+    m = c.u32_array([1])
+    assert lib.fmlp_tag_sim_f32(16, 6, 6, 16, 5, 1, rows, m, 16, 8, 0, None) == -2        # D % 4 != 0
+    assert lib.fmlp_tag_select_ws_bytes(8, 5, 100) == 8 * 5 * 2 * 100 * 8
+    assert lib.fmlp_loss_ws_bytes(32, 5) >= 4 * 2048 * 4
+
+
+def test_no_cpu_fallback():
+    import fedmlp_b200 as F
+    from fedmlp_b200._cabi import FedMLPNativeError
+    x = torch.zeros(8, 4)
+    with pytest.raises(FedMLPNativeError):
+        F.tag_similarity(x, torch.zeros(10, 4), [0])
+    with pytest.raises(FedMLPNativeError):
+        F.build_prototypes(x, torch.zeros(8, 5), None, [0], [1])
+    with pytest.raises(FedMLPNativeError):
+        F.fedmlp_stage2_loss(torch.zeros(4, 5), None, torch.zeros(4, 5), torch.zeros(4, 5))
+    if not torch.cuda.is_available():
+        with pytest.raises(FedMLPNativeError):
+            F.FedAvg([OrderedDict(w=torch.zeros(3))], [1])
+
+
+def test_flat_layout_and_densenet_shapes():
+    from fedmlp_b200.flat import FlatStateDict, flat_view_of, layout_of
+    from fedmlp_b200.shapes import count_params, densenet121_state_shapes, synth_state_dict
+    shapes = densenet121_state_shapes(5)
+    assert len(shapes) == 727 and count_params(shapes) == (7042629, 121)
+    assert count_params(densenet121_state_shapes(14)) == (7051854, 121)
+    sd = synth_state_dict(shapes, seed=1)
+    lay = layout_of(sd)
+    assert lay.n_i64 == 121 and lay.n_f32 >= 7042629 and lay.n_f32 % 4 == 0
+    flat = FlatStateDict.from_state_dict(sd)
+    assert list(flat.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(flat[k], sd[k]) and flat[k].dtype == sd[k].dtype
+    for i, k in enumerate(lay.keys):
+        if not lay.is_int[i]:
+            assert lay.offsets[i] % 4 == 0                                      # 16-byte aligned tensors
+    assert flat_view_of(flat) is not None
+    assert flat_view_of(sd) is None                                             # separately allocated tensors
+    plain = OrderedDict(flat.items())                                           # same views, plain dict
+    assert flat_view_of(plain) == flat_view_of(flat)
+    clone = flat.clone()
+    clone["classifier.bias"].add_(1)
+    assert not torch.equal(clone["classifier.bias"], flat["classifier.bias"])
+
+
+def test_fedavg_tao_host_path_matches_oracle():
+    import numpy as np
+    import fedmlp_b200 as F
+    from oracle import fedmlp_oracle as O
+    rng = np.random.default_rng(0)
+    t = [rng.random(5) for _ in range(4)]
+    w = [5000, 4999, 5001, 1234]
+    lists = [[1, 2], [0, 3], [], [0, 1, 2, 3], [2]]
+    np.testing.assert_array_equal(F.FedAvg_tao(t, w, lists), O.fedavg_tao(t, w, lists))
+    np.testing.assert_array_equal(F.FedAvg_tao(t, w), O.fedavg_tao(t, w))
