@@ -103,13 +103,19 @@ class ClientShard:
         return self._plan
 
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
-                       client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None) -> RoundResult:
+                       client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
+                       aggregate_stream=None, after_aggregate=None) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
         client_flats: S flat parameter buffers [P]; weights: S client weights (dict_len).
         All inputs are contiguous fp32 CUDA tensors on this shard's device.  The returned tensors
-        are the shard's persistent buffers (overwritten by the next round)."""
+        are the shard's persistent buffers (overwritten by the next round).
+
+        aggregate_stream: run the FedAvg stage on this side stream, forked after the loss stage so
+        it overlaps the prototype pass (both only need the locally trained weights);
+        after_aggregate(glob): called with the side stream current right after the FedAvg launch —
+        the multi-GPU driver issues its all-reduce there.  The main stream joins before returning."""
         N, C, S = self.N, self.C, self.S
         D = feat_tag.shape[1]
         if (tuple(feat_tag.shape) != (N, D) or tuple(feat_proto.shape) != (N, D) or tuple(labels.shape) != (N, C)
@@ -155,14 +161,30 @@ class ClientShard:
                                                pl.losses.data_ptr(), pl.dz.data_ptr(), pl.ws_loss.data_ptr(),
                                                pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
             mark("loss")
+
+            def fedavg_stage(stream_ptr):
+                flags = cabi.FEDAVG_DIVIDE if divide else 0
+                check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
+                                               cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
+                                               stream_ptr), "fmlp_fedavg_flat_f32")
+
+            if aggregate_stream is not None:
+                aggregate_stream.wait_stream(stream)
+                with torch.cuda.stream(aggregate_stream):
+                    fedavg_stage(aggregate_stream.cuda_stream)
+                    if after_aggregate is not None:
+                        after_aggregate(glob)
             check(lib.fmlp_proto_build_f32(feat_proto.data_ptr(), D, D, labels.data_ptr(), logits_proto.data_ptr(), 0,
                                            C, S, pl.rows, pl.active, pl.missing, self.L, self.U, 1,
                                            pl.proto.data_ptr(), pl.cnt.data_ptr(), pl.tcnt.data_ptr(),
                                            pl.ws_proto.data_ptr(), pl.ws_proto.numel(), st), "fmlp_proto_build_f32")
             mark("proto")
-            flags = cabi.FEDAVG_DIVIDE if divide else 0
-            check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]), cabi.f32_array(weights),
-                                           S, P, float(divisor), flags, glob.data_ptr(), st), "fmlp_fedavg_flat_f32")
+            if aggregate_stream is not None:
+                stream.wait_stream(aggregate_stream)
+            else:
+                fedavg_stage(st)
+                if after_aggregate is not None:
+                    after_aggregate(glob)
             mark("fedavg")
         if self.keep_history:
             # keep the lazily materialised host lists of the tagger in sync with this round's picks
