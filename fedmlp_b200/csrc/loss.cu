@@ -137,6 +137,7 @@ struct Loss2Args {
     const float *z, *zg, *y, *distill;
     float *loss, *dz;   // loss[S]
     float* ws;
+    const int32_t* seg_class_distill;  // [S][C] number of distill==1 entries per (segment, class), or null
     int64_t el_per_cta;  // elements handled by one CTA (contiguous range)
     int C;
     int variant;
@@ -161,8 +162,10 @@ __global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_
     const int s_first = e_begin < n_el ? find_segment(a.seg.rows, S, e_begin / a.C) : S;
 
     // ---- phase 1: per (CTA, segment) count of distilled entries; sup/distill are 0/1 masks, so
-    //      the denominators are exact integers
-    for (int s = s_first; s < S; ++s) {
+    //      the denominators are exact integers.  Skipped (with its grid barrier) when the caller
+    //      already knows the counts (fmlp_tag_select reports them per client and class).
+    const bool counted = a.seg_class_distill != nullptr;
+    for (int s = counted ? S : s_first; s < S; ++s) {
         const int64_t lo = max(e_begin, a.seg.rows[s] * a.C), hi = min(e_end, a.seg.rows[s + 1] * a.C);
         if (lo >= e_end) break;
         int n_dis = 0;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_
         const int b_dis = block_sum_i(n_dis, s_redi);
         if (threadIdx.x == 0) wsi[2 * kLossMaxGrid + blockIdx.x + s] = b_dis;
     }
-    grid.sync();
+    if (!counted) grid.sync();
 
     // ---- phase 2: numerators + gradient, segment by segment -----------------------------------
     for (int s = s_first; s < S; ++s) {
@@ -181,7 +184,11 @@ __global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_
         // denominator of segment s: add the counts of every CTA that touches it, in CTA order
         const int b0 = (int)(seg_lo / a.el_per_cta), b1 = (int)((seg_hi - 1) / a.el_per_cta);
         int td = 0;
-        for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) td += wsi[2 * kLossMaxGrid + b + s];
+        if (counted) {
+            if (threadIdx.x < a.C) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
+        } else {
+            for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) td += wsi[2 * kLossMaxGrid + b + s];
+        }
         td = block_sum_i(td, s_redi);
         if (threadIdx.x == 0) {
             const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
@@ -237,8 +244,10 @@ __global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_
         if (seg_hi > seg_lo) {
             const int b0 = (int)(seg_lo / a.el_per_cta), b1 = (int)((seg_hi - 1) / a.el_per_cta);
             for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) {
-                ts += a.ws[b + s]; tdis += a.ws[kLossMaxGrid + b + s]; td += wsi[2 * kLossMaxGrid + b + s];
+                ts += a.ws[b + s]; tdis += a.ws[kLossMaxGrid + b + s];
+                if (!counted) td += wsi[2 * kLossMaxGrid + b + s];
             }
+            if (counted && threadIdx.x < a.C) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
         }
         ts = block_sum(ts, s_red);
         tdis = block_sum(tdis, s_red);
@@ -312,8 +321,8 @@ extern "C" int fmlp_loss_stage1_f32(const float* z1, const float* z2, const floa
 }
 
 static int launch_loss2(const float* z, const float* zg, const float* y, const float* distill, int C, int S,
-                        const int64_t* seg_rows, int variant, float* loss, float* dz, void* ws, size_t ws_bytes,
-                        fmlp_stream_t stream) {
+                        const int64_t* seg_rows, int variant, const int32_t* seg_class_distill, float* loss, float* dz,
+                        void* ws, size_t ws_bytes, fmlp_stream_t stream) {
     if (!z || !y || !distill || !loss || !dz || !ws || C < 1 || C > FMLP_MAX_CLASSES) return FMLP_ERR_BAD_ARG;
     if (variant != FMLP_LOSS2_SUP && variant != FMLP_LOSS2_SUP_DIS) return FMLP_ERR_BAD_ARG;
     if (variant == FMLP_LOSS2_SUP_DIS && !zg) return FMLP_ERR_BAD_ARG;
@@ -322,7 +331,7 @@ static int launch_loss2(const float* z, const float* zg, const float* y, const f
     int rc = fill_seg_table(a.seg, S, seg_rows, nullptr, nullptr);
     if (rc != FMLP_OK) return rc;
     a.z = z; a.zg = zg; a.y = y; a.distill = distill; a.loss = loss; a.dz = dz; a.ws = (float*)ws;
-    a.C = C; a.variant = variant;
+    a.C = C; a.variant = variant; a.seg_class_distill = seg_class_distill;
     const int64_t n_el = seg_rows[S] * C;
     int grid = 1;
     rc = coop_grid(loss_stage2_kernel, n_el, &grid);
@@ -347,13 +356,14 @@ extern "C" int fmlp_loss_stage2_f32(const float* z, const float* zg, const float
                                     size_t ws_bytes, fmlp_stream_t stream) {
     if (B < 0) return FMLP_ERR_BAD_ARG;
     const int64_t rows[2] = {0, B};
-    return launch_loss2(z, zg, y, distill, C, 1, rows, variant, loss, dz, ws, ws_bytes, stream);
+    return launch_loss2(z, zg, y, distill, C, 1, rows, variant, nullptr, loss, dz, ws, ws_bytes, stream);
 }
 
 extern "C" int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const float* y, const float* distill,
-                                        int C, int S, const int64_t* seg_rows, int variant, float* loss,
-                                        float* dz, void* ws, size_t ws_bytes, fmlp_stream_t stream) {
-    return launch_loss2(z, zg, y, distill, C, S, seg_rows, variant, loss, dz, ws, ws_bytes, stream);
+                                        int C, int S, const int64_t* seg_rows, int variant,
+                                        const int32_t* seg_class_distill, float* loss, float* dz, void* ws,
+                                        size_t ws_bytes, fmlp_stream_t stream) {
+    return launch_loss2(z, zg, y, distill, C, S, seg_rows, variant, seg_class_distill, loss, dz, ws, ws_bytes, stream);
 }
 
 extern "C" int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream) {

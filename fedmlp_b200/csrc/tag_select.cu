@@ -18,13 +18,13 @@
 
 namespace fmlp {
 
-constexpr int kSelThreads = 512;
-constexpr int kSelBins = 2048;  // 11-bit digits; 4 bins per thread in the scan
+constexpr int kSelBins = 2048;  // 11-bit digits
 
 struct SelArgs {
     const float* sim;
     uint8_t* tag;
     int32_t* counts;     // [S][C][4]
+    int32_t* remaining;  // [S][C] candidates (tag == 0) left after this selection, or null
     int32_t* sel;        // [S][C][2][cap]
     unsigned long long* cand;  // ws [S][C][2][cap]
     int64_t ld_sim, ld_tag, cap;
@@ -33,32 +33,35 @@ struct SelArgs {
     SegTable seg;  // mask_a = missing classes
 };
 
-// Block-wide exclusive scan of one int per thread (kSelThreads threads); returns the exclusive
-// prefix and writes the grand total to *total (same value in every thread).
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp /*[kSelThreads/32 + 1]*/, int* total) {
+// Block-wide exclusive scan of a packed pair of counts (low / high 32 bits = clean / noise side);
+// returns the exclusive prefix and writes the grand total (same value in every thread).
+template <int THREADS>
+__device__ __forceinline__ unsigned long long block_exclusive_scan2(unsigned long long v, unsigned long long* s_warp,
+                                                                    unsigned long long* total) {
+    constexpr int NW = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
+    unsigned long long inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
     __syncthreads();  // s_warp reuse
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = (lane < kSelThreads / 32) ? s_warp[lane] : 0;
-        int winc = w;
+        unsigned long long w = (lane < NW) ? s_warp[lane] : 0ull;
+        unsigned long long winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= o) winc += t;
         }
-        if (lane < kSelThreads / 32) s_warp[lane] = winc - w;  // exclusive warp offsets
-        if (lane == kSelThreads / 32 - 1) s_warp[kSelThreads / 32] = winc;
+        if (lane < NW) s_warp[lane] = winc - w;  // exclusive warp offsets
+        if (lane == NW - 1) s_warp[NW] = winc;
     }
     __syncthreads();
-    *total = s_warp[kSelThreads / 32];
+    *total = s_warp[NW];
     return s_warp[warp] + inc - v;
 }
 
@@ -70,22 +73,24 @@ __device__ __forceinline__ unsigned long long make_comp(float s, uint32_t local_
 __device__ __forceinline__ int side_of(float s) { return s >= 0.f ? 0 : (s < 0.f ? 1 : -1); }
 
 // IPT > 0: every thread keeps its IPT candidate keys in registers for all passes (segments of up
-// to IPT * kSelThreads rows); IPT == 0: keys are re-read from global memory in every pass.
-// key = comp | side << 63.
-template <int IPT>
-__global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid_constant__ SelArgs a) {
+// to IPT * THREADS rows); IPT == 0: keys are re-read from global memory in every pass.
+// key = comp | side << 63.  Both sides share every histogram pass and every scan.
+template <int IPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_constant__ SelArgs a) {
     constexpr bool CACHED = IPT > 0;
     constexpr int NK = CACHED ? IPT : 1;
-    __shared__ int s_hist[2][kSelBins];  // reused as the rank staging tile (2048 x u64)
-    __shared__ int s_warp[kSelThreads / 32 + 1];
-    __shared__ int s_found[3];           // bin, remaining-in-bin, bin count
-    __shared__ int s_count[2];
+    constexpr int BPT = kSelBins / THREADS;  // bins per thread in the scan (2 or 4)
+    __shared__ int s_hist[2][kSelBins];      // reused as the rank staging tile (2048 x u64)
+    __shared__ unsigned long long s_warp[THREADS / 32 + 1];
+    __shared__ int s_found[2][3];            // per side: bin, remaining-in-bin, bin count
+    __shared__ int s_count[3];               // selected per side, candidates seen
 
     const int item = blockIdx.x;
     const int s = item / a.C, c = item - s * a.C;
     int32_t* counts = a.counts + (int64_t)item * 4;
     if (!((a.seg.mask_a[s] >> c) & 1u)) {
         if (threadIdx.x < 4) counts[threadIdx.x] = 0;
+        if (threadIdx.x == 0 && a.remaining) a.remaining[item] = 0;
         return;
     }
     const int64_t r0 = a.seg.rows[s];
@@ -93,27 +98,31 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
     const float* sim = a.sim + (int64_t)c * a.ld_sim + r0;
     uint8_t* tag = a.tag + (int64_t)c * a.ld_tag + r0;
     constexpr unsigned long long kSideBit = 1ull << 63;
+    if (threadIdx.x < 3) s_count[threadIdx.x] = 0;
 
     // ---- candidate keys ------------------------------------------------------------------
     unsigned long long key[NK];
     uint32_t valid = 0;
+    int n_cand = 0;  // tag == 0 rows (including NaN similarities, which are never picked)
     if (CACHED) {
         float v[NK];
         uint8_t tg[NK];
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            const uint32_t i = (uint32_t)k * kSelThreads + threadIdx.x;
+            const uint32_t i = (uint32_t)k * THREADS + threadIdx.x;
             const bool in = i < n;
             tg[k] = in ? tag[i] : (uint8_t)1;
             v[k] = in ? sim[i] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            const uint32_t i = (uint32_t)k * kSelThreads + threadIdx.x;
+            const uint32_t i = (uint32_t)k * THREADS + threadIdx.x;
             const int sd = side_of(v[k]);
             key[k] = make_comp(v[k], i) | (sd == 1 ? kSideBit : 0ull);
-            if (tg[k] == 0 && sd >= 0) valid |= 1u << k;
+            if (tg[k] == 0) { ++n_cand; if (sd >= 0) valid |= 1u << k; }
         }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) n_cand += tag[i] == 0 ? 1 : 0;
     }
     // visit every candidate key of this thread
     auto for_each = [&](auto&& fn) {
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
             for (int k = 0; k < NK; ++k)
                 if ((valid >> k) & 1u) fn(key[k]);
         } else {
-            for (uint32_t i = threadIdx.x; i < n; i += kSelThreads) {
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
                 if (tag[i] != 0) continue;
                 const float v = sim[i];
                 const int sd = side_of(v);
@@ -143,7 +152,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
         if (done[0] && done[1]) break;
         const int shift = pass < 5 ? 52 - 11 * pass : 0;
         const int width = pass < 5 ? 11 : 8;
-        for (int i = threadIdx.x; i < 2 * kSelBins; i += kSelThreads) (&s_hist[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < 2 * kSelBins; i += THREADS) (&s_hist[0][0])[i] = 0;
         __syncthreads();
         const unsigned long long dmask = (1ull << width) - 1ull;
         const unsigned long long pre0 = prefix[0], pre1 = prefix[1];
@@ -156,16 +165,24 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
                 atomicAdd(&s_hist[sd][(int)((comp >> shift) & dmask)], 1);
         });
         __syncthreads();
+        // bins are visited from the top: thread t owns bins 2047-BPT*t .. 2047-BPT*t-(BPT-1)
+        int h[2][BPT];
+        unsigned long long ls = 0ull;
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) {
+            const int b = kSelBins - 1 - (BPT * (int)threadIdx.x + j);
+            h[0][j] = s_hist[0][b];
+            h[1][j] = s_hist[1][b];
+            ls += (unsigned long long)(uint32_t)h[0][j] | ((unsigned long long)(uint32_t)h[1][j] << 32);
+        }
+        unsigned long long total2;
+        const unsigned long long ex2 = block_exclusive_scan2<THREADS>(ls, s_warp, &total2);
 #pragma unroll
         for (int sd = 0; sd < 2; ++sd) {
             if (done[sd]) continue;  // uniform across the CTA
-            // bins are visited from the top: thread t owns bins 2047-4t .. 2047-4t-3
-            int h[4];
-            int ls = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { h[j] = s_hist[sd][kSelBins - 1 - (4 * (int)threadIdx.x + j)]; ls += h[j]; }
-            int total;
-            const int ex = block_exclusive_scan(ls, s_warp, &total);
+            const int total = (int)(uint32_t)(total2 >> (32 * sd));
+            const int ex = (int)(uint32_t)(ex2 >> (32 * sd));
+            const int lsum = (int)(uint32_t)(ls >> (32 * sd));
             if (pass == 0) {
                 n_side[sd] = total;
                 const double frac = sd == 0 ? a.clean_frac : a.noise_frac;
@@ -176,21 +193,24 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
                 rem[sd] = (int)w;
                 if (w == 0) { done[sd] = true; continue; }
             }
-            if (ex < rem[sd] && rem[sd] <= ex + ls) {
+            if (ex < rem[sd] && rem[sd] <= ex + lsum) {
                 int cum = ex;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (cum < rem[sd] && rem[sd] <= cum + h[j]) {
-                        s_found[0] = kSelBins - 1 - (4 * (int)threadIdx.x + j);
-                        s_found[1] = rem[sd] - cum;
-                        s_found[2] = h[j];
+                for (int j = 0; j < BPT; ++j) {
+                    if (cum < rem[sd] && rem[sd] <= cum + h[sd][j]) {
+                        s_found[sd][0] = kSelBins - 1 - (BPT * (int)threadIdx.x + j);
+                        s_found[sd][1] = rem[sd] - cum;
+                        s_found[sd][2] = h[sd][j];
                     }
-                    cum += h[j];
+                    cum += h[sd][j];
                 }
             }
-            __syncthreads();
-            const int bin = s_found[0], rem_in = s_found[1], bin_count = s_found[2];
-            __syncthreads();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (done[sd]) continue;
+            const int bin = s_found[sd][0], rem_in = s_found[sd][1], bin_count = s_found[sd][2];
             prefix[sd] = (prefix[sd] << width) | (unsigned long long)bin;
             if (bin_count == rem_in) {  // whole bin is taken: threshold = smallest comp with this prefix
                 thresh[sd] = prefix[sd] << shift;
@@ -203,8 +223,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
     }
 
     // ---- compaction: mark the tag state and collect the selected comps -------------------
-    if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
-    __syncthreads();
+    n_cand = warp_sum_i(n_cand);
+    if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(&s_count[2], n_cand);
     {
         const unsigned long long t0 = thresh[0], t1 = thresh[1];
         for_each([&](unsigned long long k) {
@@ -220,6 +240,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
     __syncthreads();
     if (threadIdx.x == 0) {
         counts[0] = n_side[0]; counts[1] = n_side[1]; counts[2] = want[0]; counts[3] = want[1];
+        if (a.remaining) a.remaining[item] = s_count[2] - s_count[0] - s_count[1];
     }
 
     // ---- rank order: position = number of selected comps that are larger -----------------
@@ -229,13 +250,13 @@ __global__ void __launch_bounds__(kSelThreads, 1) tag_select_kernel(const __grid
         const int cnt = (int)min((int64_t)s_count[sd], a.cap);
         const unsigned long long* cand = a.cand + ((int64_t)item * 2 + sd) * a.cap;
         int32_t* out = a.sel + ((int64_t)item * 2 + sd) * a.cap;
-        for (int e0 = 0; e0 < cnt; e0 += kSelThreads) {
+        for (int e0 = 0; e0 < cnt; e0 += THREADS) {
             const int e = e0 + threadIdx.x;
             const unsigned long long mine = e < cnt ? cand[e] : 0ull;
             int rank = 0;
             for (int t0 = 0; t0 < cnt; t0 += kTile) {
                 __syncthreads();
-                for (int j = threadIdx.x; j < kTile && t0 + j < cnt; j += kSelThreads) tile[j] = cand[t0 + j];
+                for (int j = threadIdx.x; j < kTile && t0 + j < cnt; j += THREADS) tile[j] = cand[t0 + j];
                 __syncthreads();
                 const int lim = min(kTile, cnt - t0);
                 for (int j = 0; j < lim; ++j) rank += (tile[j] > mine) ? 1 : 0;
@@ -291,8 +312,8 @@ extern "C" size_t fmlp_tag_select_ws_bytes(int S, int C, int64_t cap) {
 
 extern "C" int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, int64_t ld_tag, int C,
                                int S, const int64_t* seg_rows, const uint32_t* seg_missing,
-                               double clean_frac, double noise_frac, int32_t* counts, int32_t* sel,
-                               int64_t cap, void* ws, size_t ws_bytes, fmlp_stream_t stream) {
+                               double clean_frac, double noise_frac, int32_t* counts, int32_t* remaining,
+                               int32_t* sel, int64_t cap, void* ws, size_t ws_bytes, fmlp_stream_t stream) {
     if (!sim || !tag || !seg_missing || !counts || !sel || !ws || C < 1 || C > FMLP_MAX_CLASSES || cap < 1)
         return FMLP_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(ws) & 7u) return FMLP_ERR_UNSUPPORTED;
@@ -303,17 +324,16 @@ extern "C" int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, i
     for (int s = 0; s < S; ++s)
         if (seg_rows[s + 1] - seg_rows[s] > 0x7fffffffLL) return FMLP_ERR_UNSUPPORTED;
     if (ld_sim < seg_rows[S] || ld_tag < seg_rows[S]) return FMLP_ERR_BAD_ARG;
-    a.sim = sim; a.tag = tag; a.counts = counts; a.sel = sel; a.cand = (unsigned long long*)ws;
+    a.sim = sim; a.tag = tag; a.counts = counts; a.remaining = remaining; a.sel = sel; a.cand = (unsigned long long*)ws;
     a.ld_sim = ld_sim; a.ld_tag = ld_tag; a.cap = cap; a.clean_frac = clean_frac; a.noise_frac = noise_frac;
     a.C = C;
     int64_t max_rows = 0;
     for (int s = 0; s < S; ++s) max_rows = std::max<int64_t>(max_rows, seg_rows[s + 1] - seg_rows[s]);
     const unsigned grid = (unsigned)(S * C);
     cudaStream_t st = (cudaStream_t)stream;
-    if (max_rows <= 8 * kSelThreads) tag_select_kernel<8><<<grid, kSelThreads, 0, st>>>(a);
-    else if (max_rows <= 16 * kSelThreads) tag_select_kernel<16><<<grid, kSelThreads, 0, st>>>(a);
-    else if (max_rows <= 32 * kSelThreads) tag_select_kernel<32><<<grid, kSelThreads, 0, st>>>(a);
-    else tag_select_kernel<0><<<grid, kSelThreads, 0, st>>>(a);
+    if (max_rows <= 8 * 1024) tag_select_kernel<8, 1024><<<grid, 1024, 0, st>>>(a);
+    else if (max_rows <= 16 * 1024) tag_select_kernel<16, 1024><<<grid, 1024, 0, st>>>(a);
+    else tag_select_kernel<0, 1024><<<grid, 1024, 0, st>>>(a);
     return launch_status();
 }
 

@@ -63,7 +63,7 @@ def launch_stage2(z, zg, y, distill, variant, loss_out, dz_out):
                                             ws.data_ptr(), ws.numel(), cabi.stream_ptr(dev)), "fmlp_loss_stage2_f32")
 
 
-def launch_stage2_seg(z, zg, y, distill, seg_rows, variant, loss_out, dz_out):
+def launch_stage2_seg(z, zg, y, distill, seg_rows, variant, loss_out, dz_out, seg_class_distill=None):
     """Raw launch of fmlp_loss_stage2_seg_f32: S clients stored back to back, one loss per client."""
     N, C = z.shape
     S = len(seg_rows) - 1
@@ -75,6 +75,7 @@ def launch_stage2_seg(z, zg, y, distill, seg_rows, variant, loss_out, dz_out):
         ws = workspace("loss", lib.fmlp_loss_ws_bytes(N, C), dev)
         cabi.check(lib.fmlp_loss_stage2_seg_f32(z.data_ptr(), None if zg is None else zg.data_ptr(), y.data_ptr(),
                                                 distill.data_ptr(), C, S, cabi.i64_array(seg_rows), variant,
+                                                None if seg_class_distill is None else seg_class_distill.data_ptr(),
                                                 loss_out.data_ptr(), dz_out.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 cabi.stream_ptr(dev)), "fmlp_loss_stage2_seg_f32")
 

@@ -52,6 +52,7 @@ class _Plan:
         cap = max(1, int(math.floor(max(shard.clean_frac, shard.noise_frac, 0.0) * max_rows)) + 1)
         self.cap = min(cap, max(max_rows, 1))
         self.counts = torch.zeros(S, C, 4, dtype=i32, device=dev)
+        self.remaining = torch.zeros(S, C, dtype=i32, device=dev)
         self.sel = torch.full((S, C, 2, self.cap), -1, dtype=i32, device=dev)
         self.y = torch.empty(N, C, dtype=f32, device=dev)
         self.distill = torch.empty(N, C, dtype=f32, device=dev)
@@ -150,7 +151,7 @@ class ClientShard:
             mark("sim")
             check(lib.fmlp_tag_select(tg.sim.data_ptr(), tg.sim.shape[1], tg.tag.data_ptr(), tg.tag.shape[1], C, S,
                                       pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),
-                                      pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(), pl.ws_select.numel(), st),
+                                      pl.remaining.data_ptr(), pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(), pl.ws_select.numel(), st),
                   "fmlp_tag_select")
             check(lib.fmlp_mask_fill(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], C, S, pl.rows, pl.active,
                                      pl.missing, pl.y.data_ptr(), pl.distill.data_ptr(), pl.sup.data_ptr(), st),
@@ -158,7 +159,7 @@ class ClientShard:
             mark("select_fill")
             check(lib.fmlp_loss_stage2_seg_f32(logits.data_ptr(), logits_glob.data_ptr(), pl.y.data_ptr(),
                                                pl.distill.data_ptr(), C, S, pl.rows, cabi.LOSS2_SUP,
-                                               pl.losses.data_ptr(), pl.dz.data_ptr(), pl.ws_loss.data_ptr(),
+                                               pl.remaining.data_ptr(), pl.losses.data_ptr(), pl.dz.data_ptr(), pl.ws_loss.data_ptr(),
                                                pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
             mark("loss")
 

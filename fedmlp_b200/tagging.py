@@ -109,6 +109,7 @@ class TagBatch:
         cap = max(1, int(math.floor(max(clean_frac, noise_frac, 0.0) * max_rows)) + 1)
         cap = min(cap, max(max_rows, 1))
         counts = torch.zeros(self.S, self.C, 4, dtype=torch.int32, device=self.device)
+        self.remaining_count = torch.zeros(self.S, self.C, dtype=torch.int32, device=self.device)
         sel = torch.full((self.S, self.C, 2, cap), -1, dtype=torch.int32, device=self.device)
         lib = cabi.lib()
         with torch.cuda.device(self.device):
@@ -124,6 +125,7 @@ class TagBatch:
                     self.C, s1 - s0, cabi.i64_array(rows),
                     cabi.u32_array([cabi.class_mask(m) for m in self.missing[s0:s1]]),
                     float(clean_frac), float(noise_frac), counts.data_ptr() + 4 * s0 * self.C * 4,
+                    self.remaining_count.data_ptr() + 4 * s0 * self.C,
                     sel.data_ptr() + 4 * s0 * self.C * 2 * cap, cap, ws.data_ptr(), ws.numel(), st),
                     "fmlp_tag_select")
                 if r0:  # rows reported by a later group are relative to that group's first row

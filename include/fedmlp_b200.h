@@ -159,14 +159,16 @@ int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const float* pro
  * positive), which is also what makes them non-candidates next round (:1197-1204).
  *   tag       [C, N_total] uint8, class-major, in/out
  *   counts    [S, C, 4] int32 out: n_clean, n_noise, m, k   (zeros for non-missing classes)
+ *   remaining [S, C] int32 out or NULL: rows that are still candidates (tag == 0) after this
+ *             selection = the number of `distill` entries of that (client, class), :1467-1468
  *   sel       [S, C, 2, cap] int32 out: global row numbers, side 0 = clean, 1 = noise
  *   cap       per-(segment,class,side) capacity; must be >= the largest possible m or k
  * ws: fmlp_tag_select_ws_bytes(S, C, cap).                                                */
 size_t fmlp_tag_select_ws_bytes(int S, int C, int64_t cap);
 int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, int64_t ld_tag, int C,
                     int S, const int64_t* seg_rows, const uint32_t* seg_missing,
-                    double clean_frac, double noise_frac, int32_t* counts, int32_t* sel,
-                    int64_t cap, void* ws, size_t ws_bytes, fmlp_stream_t stream);
+                    double clean_frac, double noise_frac, int32_t* counts, int32_t* remaining,
+                    int32_t* sel, int64_t cap, void* ws, size_t ws_bytes, fmlp_stream_t stream);
 
 /* ------------------------------------------------------------------ K3c: label / mask fill
  * Replaces DatasetSplit_pseudo.__getitem__ (utils/local_training.py:1456-1477) and
@@ -207,10 +209,14 @@ int fmlp_loss_stage2_f32(const float* z, const float* zg, const float* y, const 
                          size_t ws_bytes, fmlp_stream_t stream);
 
 /* Segmented form: S clients' rows stored back to back, each with its own denominator and its own
- * scalar loss, in one launch.  loss: device float[S].                                          */
+ * scalar loss, in one launch.  loss: device float[S].
+ * seg_class_distill: device int32 [S, C] = number of distill==1 entries per (client, class) (the
+ * `remaining` output of fmlp_tag_select), or NULL to have the kernel count them itself (one more
+ * pass over `distill` and one more grid barrier).                                               */
 int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const float* y, const float* distill,
-                             int C, int S, const int64_t* seg_rows, int variant, float* loss,
-                             float* dz, void* ws, size_t ws_bytes, fmlp_stream_t stream);
+                             int C, int S, const int64_t* seg_rows, int variant,
+                             const int32_t* seg_class_distill, float* loss, float* dz, void* ws,
+                             size_t ws_bytes, fmlp_stream_t stream);
 
 /* dz[i] *= *scale_dev  (upstream gradient of the scalar loss, read from device memory). */
 int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream);

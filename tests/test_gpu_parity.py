@@ -233,6 +233,7 @@ def test_select_vs_oracle_random(F, N, cf, nf):
         exp[ref["clean"]] = 1
         exp[ref["noise"]] = 2
         np.testing.assert_array_equal(tag[c], exp)
+        assert int(tb.remaining_count[0, c]) == int((exp == 0).sum())      # = number of distill entries
 
 
 def _assert_boundary_waiver(got, ref, ids, sims, stats):
@@ -435,6 +436,14 @@ def test_loss_stage2_segmented(F, variant):
     loss = torch.empty(len(sizes), device=DEV)
     dz = torch.empty(N, C, device=DEV)
     launch_stage2_seg(zs[0].to(DEV), zs[1].to(DEV), y.to(DEV), distill.to(DEV), seg_rows, LOSS2_VARIANTS[variant], loss, dz)
+    # same launch with the per-(client, class) distill counts supplied (what fmlp_tag_select reports):
+    # the kernel skips its counting phase and must give identical results
+    counts = torch.stack([distill[seg_rows[s]:seg_rows[s + 1]].sum(0) for s in range(len(sizes))]).to(torch.int32)
+    loss_b = torch.empty(len(sizes), device=DEV)
+    dz_b = torch.empty(N, C, device=DEV)
+    launch_stage2_seg(zs[0].to(DEV), zs[1].to(DEV), y.to(DEV), distill.to(DEV), seg_rows, LOSS2_VARIANTS[variant], loss_b, dz_b,
+                      seg_class_distill=counts.to(DEV))
+    assert torch.equal(dz_b, dz) and torch.equal(loss_b[~torch.isnan(loss_b)], loss[~torch.isnan(loss)])
     loss, dz = loss.cpu(), dz.cpu()
     for s, n in enumerate(sizes):
         r0, r1 = seg_rows[s], seg_rows[s + 1]
