@@ -52,7 +52,10 @@ struct SimCfg {
     static constexpr int THREADS = (NV <= 10) ? FMLP_SIM_THREADS_SMALL : 256;  // register caps 168 (384 thr) / 255
     static constexpr int V = R * (NV + 1);                  // values reduced per tile
     static constexpr int SCRATCH = (V + 3) & ~3;
-    static constexpr int DEPTH = 4;                         // cp.async batches in flight per warp
+#ifndef FMLP_SIM_DEPTH
+#define FMLP_SIM_DEPTH 4
+#endif
+    static constexpr int DEPTH = FMLP_SIM_DEPTH;            // cp.async batches in flight per warp
     static constexpr int RING = DEPTH * R * 128;            // floats per warp
 };
 
@@ -71,9 +74,15 @@ __device__ __forceinline__ void ldg_pairs(const float* p, u64& a, u64& b) {
 __device__ __forceinline__ void lds_pairs(uint32_t saddr, u64& a, u64& b) {
     asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
 }
-// 16-byte async copy global -> shared, L2 only (.cg); src_bytes = 0 zero-fills the destination
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination.  The .ca form
+// goes through L1, which merges the 32 lanes' 16-byte pieces into 128-byte line fills; with .cg
+// every lane pulled its own 32-byte sector from L2 and the L2->SM traffic doubled (r01 ncu:
+// l1tex__m_xbar2l1tex_read_bytes 456 MB for 225 MB of features, L2 hit rate 51 %).
+#ifndef FMLP_SIM_CPASYNC
+#define FMLP_SIM_CPASYNC "cp.async.ca.shared.global"
+#endif
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const float* g, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
+    asm volatile(FMLP_SIM_CPASYNC " [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -121,7 +130,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     using H = Halving<V>;
     extern __shared__ __align__(16) float smem[];
     const int D = a.D, Dpad = a.Dpad;
-    float* sP = smem;                                // [NV][Dpad]
+    float* sP = smem;                                // [Dpad/128][NV][128]: LDS offsets are immediates
     float* sNorm = smem + (size_t)NV * Dpad;         // [2*NPAIR] prototype norms (pair order), padded to 4
     float* sScratch = sNorm + ((2 * NPAIR + 3) & ~3);  // [warps][SCRATCH]
     float* sRing = sScratch + (size_t)(blockDim.x >> 5) * Cfg::SCRATCH;  // [warps][DEPTH][R][128]
@@ -155,7 +164,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
                 v = a.proto[(int64_t)prow * D + d];
             }
         }
-        sP[idx] = v;
+        sP[((d >> 7) * NV + j) * 128 + (d & 127)] = v;
     }
     __syncthreads();
 
@@ -173,28 +182,36 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     const int64_t tile_stride = (int64_t)gridDim.x * nwarps;
     const int64_t t_first = (int64_t)blockIdx.x * nwarps + warp;
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sRing + (size_t)warp * Cfg::RING) + lane * 16;
-    // producer cursor: batch = (tile, chunk), runs DEPTH-1 batches ahead of the math
+    // producer cursor: batch = (tile, chunk), runs DEPTH-1 batches ahead of the math.  All address
+    // arithmetic is running pointers / offsets (r01 ncu: a third of the instructions of the first
+    // ring version were IMAD/ISETP/SEL/LEA in this path); only the single ragged tile clamps rows.
     int64_t t_issue = t_first;
-    int c_issue = 0, slot_issue = 0;
+    int c_issue = 0;
+    uint32_t slot_issue = 0;                                        // byte offset of the ring slot
+    const float* g_tile = a.feat + t_first * R * a.ld_feat + lane * 4;  // row0 of the producer's tile
+    const int64_t g_stride = tile_stride * R * a.ld_feat;
+    const int64_t t_ragged = (a.n_total % R) ? n_tiles - 1 : -1;
     auto issue = [&]() {
         if (t_issue < n_tiles) {
             const int col = c_issue * 128 + lane * 4;
             const int bytes = (ALIGNED || col < D) ? 16 : 0;
-            const int64_t row0 = t_issue * R;
+            const float* g = g_tile + (bytes ? c_issue * 128 : 0);
+            if (t_issue != t_ragged) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                int64_t row = row0 + r;
-                if (row >= a.n_total) row = a.n_total - 1;  // clamp: result discarded in the epilogue
-                cp_async16(ring_addr + (uint32_t)((slot_issue * R + r) * 512), a.feat + row * a.ld_feat + (bytes ? col : 0), bytes);
+                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + r * a.ld_feat, bytes);
+            } else {
+                const int rmax = (int)(a.n_total - 1 - t_issue * R);  // rows past the end re-read the last row
+#pragma unroll
+                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + (r < rmax ? r : rmax) * a.ld_feat, bytes);
             }
-            if (++c_issue == nchunks) { c_issue = 0; t_issue += tile_stride; }
+            if (++c_issue == nchunks) { c_issue = 0; t_issue += tile_stride; g_tile += g_stride; }
         }
         cp_async_commit();  // empty groups keep the wait_group arithmetic uniform
-        slot_issue = (slot_issue + 1 == DEPTH) ? 0 : slot_issue + 1;
+        slot_issue = (slot_issue + R * 512 == DEPTH * R * 512) ? 0u : slot_issue + R * 512;
     };
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; ++d) issue();
-    int slot = 0;
+    uint32_t slot = 0;  // byte offset of the consumer's ring slot
 
     for (int64_t t = t_first; t < n_tiles; t += tile_stride) {
         const int64_t row0 = t * R;
@@ -211,13 +228,13 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
             cp_async_wait<DEPTH - 1>();  // the batch issued DEPTH-1 calls ago has landed
             u64 f0[R], f1[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) lds_pairs(ring_addr + (uint32_t)((slot * R + r) * 512), f0[r], f1[r]);
-            slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
-            const uint32_t base = sP_addr + (uint32_t)c * 512u;
+            for (int r = 0; r < R; ++r) lds_pairs(ring_addr + slot + r * 512, f0[r], f1[r]);
+            slot = (slot + R * 512 == DEPTH * R * 512) ? 0u : slot + R * 512;
+            const uint32_t base = sP_addr + (uint32_t)c * (NV * 512u);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 u64 p0, p1;
-                lds_pairs(base + (uint32_t)j * (uint32_t)Dpad * 4u, p0, p1);
+                lds_pairs(base + j * 512, p0, p1);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { fma2(acc[r][j], f0[r], p0); fma2(acc[r][j], f1[r], p1); }
             }

@@ -79,7 +79,11 @@ class ClientShard:
     keep_history = True
 
     def __init__(self, sizes, n_classes, active_classes, device=None, clean_frac=0.005, noise_frac=0.01,
-                 L=0.3, U=0.7, sim_mode="pair", dataset_idx=None):
+                 L=0.3, U=0.7, sim_mode="folded", dataset_idx=None):
+        """sim_mode: "folded" (default here: one dot product per class against
+        q_c = P0/|P0| - P1/|P1|, runs at the HBM ceiling) or "pair" (two cosines then subtract, the
+        reference's op order; FMA-co-limited for >= 4 missing classes).  They differ by O(1e-7),
+        inside the north_star waiver; both are parity-tested on the recorded reference flow."""
         self.sizes = [int(n) for n in sizes]
         self.S = len(self.sizes)
         if self.S > cabi.MAX_SEGMENTS:
@@ -105,7 +109,7 @@ class ClientShard:
 
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
-                       aggregate_stream=None, after_aggregate=None) -> RoundResult:
+                       side_stream=None, after_aggregate=None) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
@@ -113,9 +117,12 @@ class ClientShard:
         All inputs are contiguous fp32 CUDA tensors on this shard's device.  The returned tensors
         are the shard's persistent buffers (overwritten by the next round).
 
-        aggregate_stream: run the FedAvg stage on this side stream, forked after the loss stage so
-        it overlaps the prototype pass (both only need the locally trained weights);
-        after_aggregate(glob): called with the side stream current right after the FedAvg launch —
+        The pass is a DAG over its inputs: {sim -> select -> mask fill -> loss} needs the incoming
+        global model's features, {prototypes} and {FedAvg} only need the locally trained model.
+        side_stream: run prototypes + FedAvg on this stream, concurrently with the tagging/loss chain
+        (the latency-bound select / fill / loss kernels hide behind the streaming ones; in the live
+        loop the same split overlaps them with the cuDNN work around them).
+        after_aggregate(glob): called with the FedAvg stream current right after the FedAvg launch —
         the multi-GPU driver issues its all-reduce there.  The main stream joins before returning."""
         N, C, S = self.N, self.C, self.S
         D = feat_tag.shape[1]
@@ -145,48 +152,48 @@ class ClientShard:
                     e.record(stream)
                     ev[name] = e
 
+            def chain_b(stream_b):
+                sb = stream_b.cuda_stream
+                check(lib.fmlp_proto_build_f32(feat_proto.data_ptr(), D, D, labels.data_ptr(), logits_proto.data_ptr(), 0,
+                                               C, S, pl.rows, pl.active, pl.missing, self.L, self.U, 1,
+                                               pl.proto.data_ptr(), pl.cnt.data_ptr(), pl.tcnt.data_ptr(),
+                                               pl.ws_proto.data_ptr(), pl.ws_proto.numel(), sb), "fmlp_proto_build_f32")
+                if stream_b is stream:
+                    mark("proto")
+                flags = cabi.FEDAVG_DIVIDE if divide else 0
+                check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
+                                               cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
+                                               sb), "fmlp_fedavg_flat_f32")
+                if after_aggregate is not None:
+                    after_aggregate(glob)
+                if stream_b is stream:
+                    mark("fedavg")
+
             mark("start")
+            if side_stream is not None:
+                side_stream.wait_stream(stream)
+                with torch.cuda.stream(side_stream):
+                    chain_b(side_stream)
             check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
                                        tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], st), "fmlp_tag_sim_f32")
             mark("sim")
             check(lib.fmlp_tag_select(tg.sim.data_ptr(), tg.sim.shape[1], tg.tag.data_ptr(), tg.tag.shape[1], C, S,
                                       pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),
-                                      pl.remaining.data_ptr(), pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(), pl.ws_select.numel(), st),
-                  "fmlp_tag_select")
+                                      pl.remaining.data_ptr(), pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(),
+                                      pl.ws_select.numel(), st), "fmlp_tag_select")
             check(lib.fmlp_mask_fill(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], C, S, pl.rows, pl.active,
                                      pl.missing, pl.y.data_ptr(), pl.distill.data_ptr(), pl.sup.data_ptr(), st),
                   "fmlp_mask_fill")
             mark("select_fill")
             check(lib.fmlp_loss_stage2_seg_f32(logits.data_ptr(), logits_glob.data_ptr(), pl.y.data_ptr(),
                                                pl.distill.data_ptr(), C, S, pl.rows, cabi.LOSS2_SUP,
-                                               pl.remaining.data_ptr(), pl.losses.data_ptr(), pl.dz.data_ptr(), pl.ws_loss.data_ptr(),
-                                               pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
+                                               pl.remaining.data_ptr(), pl.losses.data_ptr(), pl.dz.data_ptr(),
+                                               pl.ws_loss.data_ptr(), pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
             mark("loss")
-
-            def fedavg_stage(stream_ptr):
-                flags = cabi.FEDAVG_DIVIDE if divide else 0
-                check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
-                                               cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
-                                               stream_ptr), "fmlp_fedavg_flat_f32")
-
-            if aggregate_stream is not None:
-                aggregate_stream.wait_stream(stream)
-                with torch.cuda.stream(aggregate_stream):
-                    fedavg_stage(aggregate_stream.cuda_stream)
-                    if after_aggregate is not None:
-                        after_aggregate(glob)
-            check(lib.fmlp_proto_build_f32(feat_proto.data_ptr(), D, D, labels.data_ptr(), logits_proto.data_ptr(), 0,
-                                           C, S, pl.rows, pl.active, pl.missing, self.L, self.U, 1,
-                                           pl.proto.data_ptr(), pl.cnt.data_ptr(), pl.tcnt.data_ptr(),
-                                           pl.ws_proto.data_ptr(), pl.ws_proto.numel(), st), "fmlp_proto_build_f32")
-            mark("proto")
-            if aggregate_stream is not None:
-                stream.wait_stream(aggregate_stream)
+            if side_stream is not None:
+                stream.wait_stream(side_stream)
             else:
-                fedavg_stage(st)
-                if after_aggregate is not None:
-                    after_aggregate(glob)
-            mark("fedavg")
+                chain_b(stream)
         if self.keep_history:
             # keep the lazily materialised host lists of the tagger in sync with this round's picks
             tg._history.append((pl.counts.clone(), pl.sel.clone(), pl.cap))

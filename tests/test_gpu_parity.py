@@ -474,9 +474,11 @@ def test_losses_golden_flow(F):
 
 
 # =============================================================================== recorded flow, end to end
-def test_golden_flow_tagging_and_prototypes(F):
+@pytest.mark.parametrize("mode", ["pair", "folded"])
+def test_golden_flow_tagging_and_prototypes(F, mode):
     """Replay the reference's recorded stage-2 rounds through the CUDA path: same selected
-    indices (traindata_idx, in pick order), same remaining sets, same masks, same prototypes/t."""
+    indices (traindata_idx, in pick order), same remaining sets, same masks, same prototypes/t —
+    with either similarity formulation."""
     flow = gu.load("flow.npz")
     neg, act = flow["s1/neg_list"].tolist(), flow["s1/act_list"].tolist()
     C = int(flow["meta/C"])
@@ -496,7 +498,7 @@ def test_golden_flow_tagging_and_prototypes(F):
         idx_r, _, feat_r, _ = rd["extract"]
         order = {int(d): p for p, d in enumerate(idx_r.tolist())}
         perm = [order[int(d)] for d in idx0.tolist()]
-        tb.step(cuda(feat_r[perm]), proto_glob, cf, nf)
+        tb.step(cuda(feat_r[perm]), proto_glob, cf, nf, mode=mode)
         got = tb.traindata_idx(0)
         for j in range(2 * len(neg)):
             assert got[j] == flow[f"s2_{r}/traindata_idx/{j}"].tolist()
