@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused fold+all-reduce kernel over peer memory, or local fold + NCCL all-reduce")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     return ap.parse_args()
 
@@ -309,6 +311,17 @@ def gpu_arm(a):
         w_norm = [w / total_w for w in inp["weights"]]          # pre-normalised: all-reduce yields the mean
 
     side_stream = torch.cuda.Stream(device=dev)
+    fused, collective = None, "none"
+    if world > 1:
+        collective = "nccl all_reduce after the local fold"
+        if a.collective == "fused":
+            try:
+                from fedmlp_b200.dist import FusedFedAvgAllReduce
+                fused = FusedFedAvgAllReduce(inp["Ppad"], device=dev)
+                collective = "fused fold + two-shot all-reduce over NVLink peer memory (one kernel per rank)"
+            except Exception as exc:
+                fused = None
+                collective += f" (fused path unavailable: {type(exc).__name__}: {exc})"[:200]
 
     def step(timers=None, overlap=True):
         """One round hot path.  overlap: {prototypes -> FedAvg (-> all-reduce)} on a side stream,
@@ -319,6 +332,11 @@ def gpu_arm(a):
             return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
                                         inp["feat_proto"], inp["logits_proto"], inp["flats"], inp["weights"],
                                         timers=timers, fedavg_out=fed_out, side_stream=side)
+        if fused is not None:
+            return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
+                                        inp["feat_proto"], inp["logits_proto"], inp["flats"], w_norm, timers=timers,
+                                        fedavg_out=fed_out, divide=False, side_stream=side,
+                                        aggregate_fn=lambda bufs, w: fused(bufs, w))
         return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
                                     inp["feat_proto"], inp["logits_proto"], inp["flats"], w_norm, timers=timers,
                                     fedavg_out=fed_out, divide=False, side_stream=side,
@@ -338,6 +356,8 @@ def gpu_arm(a):
     #      the launch-bound inner loop is captured once, as the task's design rules ask)
     graph, graph_note = None, "eager launches"
     launches_per_step = None
+    # N>1 stays eager: a graph serialises the cooperative fold+all-reduce kernel against the other
+    # stream (measured slower) and NCCL capture is not used
     if world == 1 and not a.no_graph:
         try:
             l0 = lib.fmlp_launch_count()
@@ -345,7 +365,8 @@ def gpu_arm(a):
             with torch.cuda.graph(g_):
                 step()
             launches_per_step = lib.fmlp_launch_count() - l0
-            graph, graph_note = g_, "CUDA-graph replay of the 7-launch round, two-stream DAG {sim,select,fill,loss} || {proto,FedAvg}"
+            graph, graph_note = g_, ("CUDA-graph replay of the 7-launch round, two-stream DAG {sim,select,fill,loss} || {proto,FedAvg"
+                                     + ("+all-reduce}" if world > 1 else "}"))
             for _ in range(3):
                 graph.replay()
         except Exception as exc:          # fall back to eager timing, say so
@@ -395,8 +416,9 @@ def gpu_arm(a):
         gbs = ab[k] / (kms[k] * 1e-3) / 1e9
         kernels[k] = {"ms": round(kms[k], 5), "alg_bytes": ab[k], "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
     if world > 1:
-        kernels["fedavg"]["note"] = "FedAvg partial + NCCL all-reduce (timed back to back on one stream here)"
-        kernels["allreduce_alone"] = measure_allreduce(fed_out, world)
+        kernels["fedavg"]["note"] = collective
+        kernels["fedavg"].pop("gbs", None); kernels["fedavg"].pop("frac_of_hbm_peak", None)
+        kernels["nccl_allreduce_alone"] = measure_allreduce(fed_out, world)
     dom = max(("sim", "proto", "fedavg") if world == 1 else ("sim", "proto"), key=lambda k: kms[k])
     dom_names = {"sim": "tag_sim_kernel", "proto": "proto_accum_kernel", "fedavg": "fedavg_flat_kernel"}
     roofline = {"kernel": dom_names[dom], "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
@@ -427,8 +449,8 @@ def gpu_arm(a):
                        "l2": f"inputs larger than L2: {round((ab['sim'] + ab['proto'] + ab['fedavg']) / 1e6)} MB streamed per step vs 126 MB L2, no flush needed",
                        "parallelism": (f"clients sharded over {world} GPU(s); FedAvg = local weighted partial + NCCL all-reduce, "
                                        "on a side stream with the prototype pass, concurrent with the tagging/loss chain")
-                       if world > 1 else "single GPU"},
-            "fedavg_gbs": kernels["fedavg"]["gbs"],
+                       if world > 1 else "single GPU", "collective": collective},
+            "fedavg_gbs": kernels["fedavg"].get("gbs"),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps, "clocks": clocks,
             "timing": {"value": graph_note, "kernels": "eager launches, CUDA event after every stage",

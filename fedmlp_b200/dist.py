@@ -75,6 +75,61 @@ def fedavg_flat_distributed(local_bufs, local_weights, total_weight=None, out=No
     return partial
 
 
+class FusedFedAvgAllReduce:
+    """Local K-way weighted fold + two-shot all-reduce over NVLink peer memory in ONE kernel per
+    rank (fedavg_allreduce.cu).  Symmetric-memory buffers are allocated and exchanged once; every
+    call is a single cooperative launch on the current stream.  Collective: all ranks call it with
+    the same P.  Needs NVLink/P2P between the ranks' GPUs (torch symmetric memory)."""
+
+    def __init__(self, P: int, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("FusedFedAvgAllReduce supports up to 8 ranks (one NVSwitch domain)")
+        if P % 4:
+            raise ValueError("P must be a multiple of 4 (flat buffers are 16-byte padded)")
+        self.P = int(P)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        L = (self.P + self.world - 1) // self.world
+        self.L = (L + 3) // 4 * 4
+        n = self.world * self.L
+        self.stage = symm.empty(n, dtype=torch.float32, device=self.device)
+        self.result = symm.empty(n, dtype=torch.float32, device=self.device)
+        self.flags = symm.empty(16, dtype=torch.int32, device=self.device)
+        self.stage.zero_(); self.result.zero_(); self.flags.zero_()
+        hs = symm.rendezvous(self.stage, self.group)
+        hr = symm.rendezvous(self.result, self.group)
+        hf = symm.rendezvous(self.flags, self.group)
+        self._handles = (hs, hr, hf)
+        self.stage_ptrs = cabi.ptr_array(list(hs.buffer_ptrs))
+        self.result_ptrs = cabi.ptr_array(list(hr.buffer_ptrs))
+        self.flag_ptrs = cabi.ptr_array(list(hf.buffer_ptrs))
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.device)   # per-rank call counter
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)          # every rank's flags are zero before anyone signals
+
+    def __call__(self, local_bufs, weights_normalised):
+        """Returns the [P] global weighted mean (a view of this rank's symmetric result buffer,
+        overwritten by the next call)."""
+        K = len(local_bufs)
+        if not 1 <= K <= cabi.MAX_CLIENTS:
+            raise ValueError(f"1..{cabi.MAX_CLIENTS} clients per rank")
+        cabi.require_cuda(*local_bufs)
+        for b in local_bufs:
+            if b.numel() != self.P or b.dtype != torch.float32 or not b.is_contiguous():
+                raise ValueError("client buffers must be contiguous float32 of length P")
+        with torch.cuda.device(self.device):
+            cabi.check(cabi.lib().fmlp_fedavg_allreduce_f32(
+                cabi.ptr_array([b.data_ptr() for b in local_bufs]), cabi.f32_array(weights_normalised), K, self.P,
+                self.stage_ptrs, self.result_ptrs, self.flag_ptrs, self.L, self.rank, self.world,
+                self.epoch_dev.data_ptr(),
+                cabi.stream_ptr(self.device)), "fmlp_fedavg_allreduce_f32")
+        return self.result[:self.P]
+
+
 def FedAvg_distributed(w_local, dict_len_local, group=None, total_weight=None, local_reduce=None):
     """Distributed drop-in for FedAvg(w, dict_len) (reference utils/FedAvg.py:7-14): every rank
     passes the state_dicts and weights of ITS clients; all ranks get the same averaged dict

@@ -109,7 +109,7 @@ class ClientShard:
 
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
-                       side_stream=None, after_aggregate=None) -> RoundResult:
+                       side_stream=None, after_aggregate=None, aggregate_fn=None) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
@@ -123,7 +123,9 @@ class ClientShard:
         (the latency-bound select / fill / loss kernels hide behind the streaming ones; in the live
         loop the same split overlaps them with the cuDNN work around them).
         after_aggregate(glob): called with the FedAvg stream current right after the FedAvg launch —
-        the multi-GPU driver issues its all-reduce there.  The main stream joins before returning."""
+        the multi-GPU driver issues its all-reduce there.  The main stream joins before returning.
+        aggregate_fn(client_flats, weights) -> [P] tensor: replaces the FedAvg launch altogether (the
+        fused fold + all-reduce kernel of dist.FusedFedAvgAllReduce)."""
         N, C, S = self.N, self.C, self.S
         D = feat_tag.shape[1]
         if (tuple(feat_tag.shape) != (N, D) or tuple(feat_proto.shape) != (N, D) or tuple(labels.shape) != (N, C)
@@ -152,6 +154,8 @@ class ClientShard:
                     e.record(stream)
                     ev[name] = e
 
+            out = {"glob": glob}
+
             def chain_b(stream_b):
                 sb = stream_b.cuda_stream
                 check(lib.fmlp_proto_build_f32(feat_proto.data_ptr(), D, D, labels.data_ptr(), logits_proto.data_ptr(), 0,
@@ -160,12 +164,15 @@ class ClientShard:
                                                pl.ws_proto.data_ptr(), pl.ws_proto.numel(), sb), "fmlp_proto_build_f32")
                 if stream_b is stream:
                     mark("proto")
-                flags = cabi.FEDAVG_DIVIDE if divide else 0
-                check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
-                                               cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
-                                               sb), "fmlp_fedavg_flat_f32")
-                if after_aggregate is not None:
-                    after_aggregate(glob)
+                if aggregate_fn is not None:
+                    out["glob"] = aggregate_fn(client_flats, weights)
+                else:
+                    flags = cabi.FEDAVG_DIVIDE if divide else 0
+                    check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
+                                                   cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
+                                                   sb), "fmlp_fedavg_flat_f32")
+                    if after_aggregate is not None:
+                        after_aggregate(glob)
                 if stream_b is stream:
                     mark("fedavg")
 
@@ -199,4 +206,4 @@ class ClientShard:
             tg._history.append((pl.counts.clone(), pl.sel.clone(), pl.cap))
         tg._lists = None
         return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz,
-                           PrototypeResult(pl.proto, pl.cnt, pl.tcnt, list(self.seg_rows)), glob, ev)
+                           PrototypeResult(pl.proto, pl.cnt, pl.tcnt, list(self.seg_rows)), out["glob"], ev)

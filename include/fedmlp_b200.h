@@ -101,6 +101,25 @@ int fmlp_fedavg_multi_i64(const int64_t* const* src_table_dev, float* const* dst
                           int64_t J, int T, const double* weights, int K, double divisor,
                           int weights_integral, int flags, fmlp_stream_t stream);
 
+/* Multi-GPU FedAvg in ONE kernel per rank: K-way weighted fold of this rank's client buffers fused
+ * with a two-shot all-reduce over NVLink peer memory (reduce-scatter by peer stores that overlap
+ * the HBM-bound fold, fixed-order slice reduction, all-gather by peer stores).  There is no
+ * reference counterpart (the reference is single-process, main.py:130,196); semantics = the global
+ * weighted mean of utils/FedAvg.py:7-14 over the clients of all ranks.
+ *   srcs / weights   host arrays [K]: this rank's client buffers (P floats each, 16-B aligned) and
+ *                    their weights PRE-NORMALISED by the global sum (n_k / sum over all ranks)
+ *   stage_ptrs       host array [world]: every rank's inbox   (symmetric memory, world*slice_len floats)
+ *   result_ptrs      host array [world]: every rank's result buffer (>= world*slice_len floats)
+ *   flag_ptrs        host array [world]: every rank's flag words (16 x uint32, zero-initialised once)
+ *   slice_len        floats per rank slice, multiple of 4, world*slice_len >= P;  P % 4 == 0
+ *   epoch_dev        device uint32 of THIS rank, zero-initialised once; the kernel uses *epoch_dev+1
+ *                    as the call's epoch and stores it back (so CUDA-graph replays stay in step)
+ * Collective: every rank must launch it; the kernel returns when result_ptrs[rank] is complete. */
+int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* weights, int K, int64_t P,
+                              float* const* stage_ptrs, float* const* result_ptrs,
+                              uint32_t* const* flag_ptrs, int64_t slice_len, int rank, int world,
+                              uint32_t* epoch_dev, fmlp_stream_t stream);
+
 /* Prototype aggregation, replaces utils/FedAvg.py:72-93 `FedAvg_proto`:
  *   out[2c+j] = (sum over clients i in act(c), in list order, of protos[i][2c+j]*n_i) / sum n_i
  * protos  device [K][2C][D] (stacked client prototypes);  weights host [K];
