@@ -9,7 +9,8 @@ All arithmetic runs in hand-written CUDA kernels (fedmlp_b200/csrc, C ABI in inc
 loaded through ctypes; there is no CPU / PyTorch fallback.
 """
 from . import _cabi
-from .fedavg import FedAvg, Fed_w, FedAvg_proto, FedAvg_tao, fedavg_flat_buffers
+from .fedavg import (DaAgg, FedAvg, FedAvg_proto, FedAvg_rela, FedAvg_tao, Fed_w, RSCFed, fedavg_flat_buffers,
+                     model_dist)
 from .flat import FlatLayout, FlatStateDict, flatten_module_, layout_of
 from .losses import (fedmlp_stage1_loss, fedmlp_stage2_loss, fused_loss_and_grad_stage1,
                      fused_loss_and_grad_stage2)
@@ -17,7 +18,7 @@ from .prototypes import PrototypeResult, build_prototypes
 from .tagging import TagBatch, tag_similarity
 
 __all__ = [
-    "FedAvg", "Fed_w", "FedAvg_proto", "FedAvg_tao", "fedavg_flat_buffers",
+    "FedAvg", "Fed_w", "FedAvg_proto", "FedAvg_tao", "FedAvg_rela", "RSCFed", "DaAgg", "model_dist", "fedavg_flat_buffers",
     "FlatLayout", "FlatStateDict", "flatten_module_", "layout_of",
     "fedmlp_stage1_loss", "fedmlp_stage2_loss", "fused_loss_and_grad_stage1", "fused_loss_and_grad_stage2",
     "PrototypeResult", "build_prototypes", "TagBatch", "tag_similarity",

@@ -268,7 +268,7 @@ struct ProtoAvgArgs {
     float w[FMLP_MAX_CLIENTS];
     float class_div[FMLP_MAX_CLASSES];  // fp32(sum of the ORIGINAL weights over act(c))
     uint64_t class_clients[FMLP_MAX_CLASSES];
-    int K, C, D;
+    int K, C, D, rpc;  // rpc = rows per class: 2 for FedAvg_proto, 1 for FedAvg_rela
 };
 
 // grid.x = 2C rows; FedAvg.py:79-86: acc = P_i*w_i + acc over act(c) in list (= ascending
@@ -277,17 +277,73 @@ struct ProtoAvgArgs {
 // which is what torch does with a numpy scalar divisor.
 __global__ void __launch_bounds__(256) proto_avg_kernel(const __grid_constant__ ProtoAvgArgs a) {
     const int row = blockIdx.x;
-    const int c = row >> 1;
+    const int c = row / a.rpc;
     const uint64_t members = a.class_clients[c];
     const float divisor = a.class_div[c];
     const int64_t row_off = (int64_t)row * a.D;
-    const int64_t client_stride = (int64_t)2 * a.C * a.D;
+    const int64_t client_stride = (int64_t)a.rpc * a.C * a.D;
     for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
         float acc = 0.f;
         for (int i = 0; i < a.K; ++i)
             if ((members >> i) & 1ull)
                 acc = __fadd_rn(__fmul_rn(a.protos[i * client_stride + row_off + d], a.w[i]), acc);
         a.out[row_off + d] = __fdiv_rn(acc, divisor);
+    }
+}
+
+// ---------------------------------------------------------------- model_dist
+// utils/FedNoRo.py:106-115 (and utils/FedAvg.py:42-49): sum over the float tensors, in key order,
+// of ||w1[k] - w2[k]||_2.  Deterministic: per-chunk sums of squares (fixed tree inside the CTA),
+// per-tensor chunk sums in chunk order, then ONE thread adds the per-tensor norms in key order
+// exactly like the reference's `dist_total += dist` loop.
+struct ModelDistArgs {
+    const float* const* a_table;    // [T]
+    const float* const* b_table;    // [T]
+    const int64_t* numel;           // [T]
+    const int32_t* chunk_tensor;    // [n_chunks]
+    const int64_t* chunk_start;     // [n_chunks]
+    const int64_t* tensor_chunk0;   // [T+1] first chunk of every tensor
+    float* partial;                 // ws [n_chunks + T]
+    float* out;                     // [1]
+    int64_t n_chunks;
+    int T;
+};
+
+__global__ void __launch_bounds__(256) model_dist_partial_kernel(const __grid_constant__ ModelDistArgs a) {
+    __shared__ float s_red[8];
+    for (int64_t c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
+        const int t = a.chunk_tensor[c];
+        const int64_t start = a.chunk_start[c];
+        const int64_t len = min((int64_t)FMLP_FEDAVG_CHUNK, a.numel[t] - start);
+        const float* x = a.a_table[t] + start;
+        const float* y = a.b_table[t] + start;
+        float ss = 0.f;
+        for (int64_t e = threadIdx.x; e < len; e += 256) { const float d = __fsub_rn(x[e], y[e]); ss = fmaf(d, d, ss); }
+        ss = warp_sum(ss);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_red[w];
+            a.partial[c] = tot;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) model_dist_finalize_kernel(const __grid_constant__ ModelDistArgs a) {
+    float* norms = a.partial + a.n_chunks;
+    for (int t = threadIdx.x; t < a.T; t += 256) {
+        float ss = 0.f;
+        for (int64_t c = a.tensor_chunk0[t]; c < a.tensor_chunk0[t + 1]; ++c) ss += a.partial[c];
+        norms[t] = sqrtf(ss);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+        for (int t = 0; t < a.T; ++t) total = __fadd_rn(total, norms[t]);
+        a.out[0] = total;
     }
 }
 
@@ -389,13 +445,14 @@ extern "C" int fmlp_fedavg_multi_i64(const int64_t* const* src_table_dev, float*
     return launch_status();
 }
 
-extern "C" int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, const double* weights,
-                                  const uint64_t* class_clients, float* out, fmlp_stream_t stream) {
+extern "C" int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, int rows_per_class,
+                                  const double* weights, const uint64_t* class_clients, float* out,
+                                  fmlp_stream_t stream) {
     if (!protos || !weights || !class_clients || !out || C < 1 || C > FMLP_MAX_CLASSES || D < 1 ||
-        check_k(K) != FMLP_OK)
+        (rows_per_class != 1 && rows_per_class != 2) || check_k(K) != FMLP_OK)
         return FMLP_ERR_BAD_ARG;
     ProtoAvgArgs a;
-    a.protos = protos; a.out = out; a.K = K; a.C = C; a.D = D;
+    a.protos = protos; a.out = out; a.K = K; a.C = C; a.D = D; a.rpc = rows_per_class;
     for (int i = 0; i < FMLP_MAX_CLIENTS; ++i) a.w[i] = i < K ? (float)weights[i] : 0.f;
     for (int c = 0; c < FMLP_MAX_CLASSES; ++c) {
         a.class_clients[c] = c < C ? class_clients[c] : 0ull;
@@ -404,6 +461,36 @@ extern "C" int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, cons
             if (c < C && ((class_clients[c] >> i) & 1ull)) wsum += weights[i];
         a.class_div[c] = (float)wsum;
     }
-    proto_avg_kernel<<<2 * C, 256, 0, (cudaStream_t)stream>>>(a);
+    proto_avg_kernel<<<rows_per_class * C, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status();
+}
+
+extern "C" size_t fmlp_model_dist_ws_bytes(int64_t n_chunks, int T) {
+    return (size_t)((n_chunks > 0 ? n_chunks : 0) + (T > 0 ? T : 0) + 1) * sizeof(float);
+}
+
+extern "C" int fmlp_model_dist_f32(const float* const* a_table_dev, const float* const* b_table_dev,
+                                   const int64_t* numel_dev, const int32_t* chunk_tensor_dev,
+                                   const int64_t* chunk_start_dev, const int64_t* tensor_chunk0_dev,
+                                   int64_t n_chunks, int T, float* out, void* ws, size_t ws_bytes,
+                                   fmlp_stream_t stream) {
+    if (!a_table_dev || !b_table_dev || !numel_dev || !chunk_tensor_dev || !chunk_start_dev || !tensor_chunk0_dev ||
+        !out || !ws || n_chunks < 0 || T < 0)
+        return FMLP_ERR_BAD_ARG;
+    if (ws_bytes < fmlp_model_dist_ws_bytes(n_chunks, T)) return FMLP_ERR_WORKSPACE;
+    ModelDistArgs a;
+    a.a_table = a_table_dev; a.b_table = b_table_dev; a.numel = numel_dev; a.chunk_tensor = chunk_tensor_dev;
+    a.chunk_start = chunk_start_dev; a.tensor_chunk0 = tensor_chunk0_dev; a.partial = (float*)ws; a.out = out;
+    a.n_chunks = n_chunks; a.T = T;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_chunks > 0) {
+        const int sms = sm_count();
+        if (sms <= 0) return (int)cudaErrorInvalidDevice;
+        int64_t blocks = n_chunks < (int64_t)sms * 8 ? n_chunks : (int64_t)sms * 8;
+        model_dist_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+        int rc = launch_status();
+        if (rc != FMLP_OK) return rc;
+    }
+    model_dist_finalize_kernel<<<1, 256, 0, st>>>(a);
     return launch_status();
 }

@@ -35,12 +35,14 @@ def _multi_plan(layout: FlatLayout, device):
     if plan is not None:
         return plan
     f_idx, i_idx = layout.float_index, layout.int_index
-    chunk_tensor, chunk_start = [], []
+    chunk_tensor, chunk_start, tensor_chunk0 = [], [], []
     for t, i in enumerate(f_idx):
         n = layout.numels[i]
+        tensor_chunk0.append(len(chunk_tensor))
         for s in range(0, n, cabi.FEDAVG_CHUNK):
             chunk_tensor.append(t)
             chunk_start.append(s)
+    tensor_chunk0.append(len(chunk_tensor))
     elem_tensor, elem_index = [], []
     for t, i in enumerate(i_idx):
         for e in range(layout.numels[i]):
@@ -52,6 +54,7 @@ def _multi_plan(layout: FlatLayout, device):
         chunk_tensor=torch.tensor(chunk_tensor, dtype=torch.int32, device=device),
         chunk_start=torch.tensor(chunk_start, dtype=torch.int64, device=device),
         n_chunks=len(chunk_tensor),
+        tensor_chunk0=torch.tensor(tensor_chunk0, dtype=torch.int64, device=device),
         elem_tensor=torch.tensor(elem_tensor, dtype=torch.int32, device=device),
         elem_index=torch.tensor(elem_index, dtype=torch.int64, device=device),
         n_elems=len(elem_tensor),
@@ -99,7 +102,7 @@ def fedavg_flat_buffers(bufs, weights, out=None, divisor=None, divide=True):
     return out
 
 
-def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev):
+def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev, div_flag=cabi.FEDAVG_DIVIDE):
     lib = cabi.lib()
     K = len(ptrs)
     if K > cabi.MAX_CLIENTS and integral:
@@ -107,18 +110,20 @@ def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev):
     st = cabi.stream_ptr(dev)
     for g0 in range(0, K, cabi.MAX_CLIENTS):
         g1 = min(K, g0 + cabi.MAX_CLIENTS)
-        flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (cabi.FEDAVG_DIVIDE if g1 == K else 0)
+        flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (div_flag if g1 == K else 0)
         cabi.check(lib.fmlp_fedavg_flat_i64(cabi.ptr_array(ptrs[g0:g1]), cabi.f64_array(weights[g0:g1]), g1 - g0, J,
                                             float(divisor), 1 if integral else 0, flags, out_ptr, st),
                    "fmlp_fedavg_flat_i64")
 
 
-def _fedavg_cuda(w, dict_len):
+def _fedavg_cuda(w, dict_len, divide=True):
+    """divide=False: plain weighted sum (DaAgg, utils/FedNoRo.py:98-103)."""
     layout = layout_of(w[0])
     dev = next(iter(w[0].values())).device
     K = len(w)
     integral = all(_is_integral(x) for x in dict_len)
-    divisor = sum(dict_len)
+    divisor = sum(dict_len) if divide else 1.0
+    div_flag = cabi.FEDAVG_DIVIDE if divide else 0
     out = FlatStateDict.empty(layout, dev, ints_as_float=True)
     lib = cabi.lib()
     with torch.cuda.device(dev):
@@ -130,13 +135,13 @@ def _fedavg_cuda(w, dict_len):
                 bufs = [v[0] for v in views]
                 for g0 in range(0, K, cabi.MAX_CLIENTS):
                     g1 = min(K, g0 + cabi.MAX_CLIENTS)
-                    flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (cabi.FEDAVG_DIVIDE if g1 == K else 0)
+                    flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (div_flag if g1 == K else 0)
                     cabi.check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array(bufs[g0:g1]), cabi.f32_array(dict_len[g0:g1]),
                                                         g1 - g0, layout.n_f32, float(divisor), flags,
                                                         out.flat_f32.data_ptr(), st), "fmlp_fedavg_flat_f32")
             if layout.n_i64:
                 _fedavg_i64_flat([v[1] for v in views], list(dict_len), layout.n_i64, divisor, integral,
-                                 out.flat_f32.data_ptr() + 4 * layout.n_f32, dev)
+                                 out.flat_f32.data_ptr() + 4 * layout.n_f32, dev, div_flag)
             return out
         # ---- multi-tensor path: read the scattered tensors in place ---------------------
         plan = _multi_plan(layout, dev)
@@ -167,12 +172,12 @@ def _fedavg_cuda(w, dict_len):
             cabi.check(lib.fmlp_fedavg_multi_f32(base, base + 8 * Tf * K, plan["numel"].data_ptr(),
                                                  plan["chunk_tensor"].data_ptr(), plan["chunk_start"].data_ptr(),
                                                  plan["n_chunks"], Tf, cabi.f32_array(dict_len), K, float(divisor),
-                                                 cabi.FEDAVG_DIVIDE, st), "fmlp_fedavg_multi_f32")
+                                                 div_flag, st), "fmlp_fedavg_multi_f32")
         if Ti:
             cabi.check(lib.fmlp_fedavg_multi_i64(base + 8 * o, base + 8 * (o + Ti * K), plan["elem_tensor"].data_ptr(),
                                                  plan["elem_index"].data_ptr(), plan["n_elems"], Ti,
                                                  cabi.f64_array(dict_len), K, float(divisor), 1 if integral else 0,
-                                                 cabi.FEDAVG_DIVIDE, st), "fmlp_fedavg_multi_i64")
+                                                 div_flag, st), "fmlp_fedavg_multi_i64")
         out._keepalive = table_dev  # the launch is asynchronous; keep the table until the dict dies
     return out
 
@@ -197,7 +202,7 @@ def _stage_cpu_client(sd, dev):
     return d
 
 
-def FedAvg(w, dict_len):
+def FedAvg(w, dict_len, _divide=True):
     """Weighted average of K client state_dicts (reference utils/FedAvg.py:7-14).
 
     w: list of K OrderedDict[str, Tensor] with identical keys; dict_len: K ints or floats.
@@ -213,12 +218,12 @@ def FedAvg(w, dict_len):
     if first.is_cuda:
         for sd in w:
             cabi.require_cuda(*sd.values())
-        return _fedavg_cuda(w, dict_len)
+        return _fedavg_cuda(w, dict_len, _divide)
     if not torch.cuda.is_available():
         raise cabi.FedMLPNativeError("FedAvg needs a CUDA device (fedmlp_b200 has no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
     staged = [_stage_cpu_client(sd, dev) for sd in w]
-    res = _fedavg_cuda(staged, dict_len)
+    res = _fedavg_cuda(staged, dict_len, _divide)
     host_flat = res.flat_f32.cpu()
     out = OrderedDict()
     lay = res.layout
@@ -234,7 +239,7 @@ def Fed_w(w, weight):
     return FedAvg(w, weight)
 
 
-def FedAvg_proto(Prototypes, weight, class_active_client_list):
+def FedAvg_proto(Prototypes, weight, class_active_client_list, _rows_per_class=2):
     """Per-class weighted mean of the clients' prototypes (reference utils/FedAvg.py:72-93).
     Prototypes: list of K [2C, D] tensors; returns [2C, D] on the device of the inputs
     (the reference works on CPU tensors and returns a CPU tensor)."""
@@ -249,8 +254,9 @@ def FedAvg_proto(Prototypes, weight, class_active_client_list):
         raise cabi.FedMLPNativeError("FedAvg_proto needs a CUDA device (no CPU fallback)")
     dev = p0.device if p0.is_cuda else torch.device("cuda", torch.cuda.current_device())
     stacked = torch.stack([p.to(dev, dtype=torch.float32) for p in Prototypes]).contiguous()
+    rpc = _rows_per_class
     C2, D = stacked.shape[1], stacked.shape[2]
-    C = C2 // 2
+    C = C2 // rpc
     if len(class_active_client_list) > C:
         raise ValueError("class_active_client_list longer than the number of classes")
     masks = [0] * C
@@ -264,11 +270,87 @@ def FedAvg_proto(Prototypes, weight, class_active_client_list):
     n_listed = len(class_active_client_list)
     with torch.cuda.device(dev):
         tmp = torch.empty(C2, D, dtype=torch.float32, device=dev)
-        cabi.check(cabi.lib().fmlp_proto_avg_f32(stacked.data_ptr(), K, C, D, cabi.f64_array(weight),
+        cabi.check(cabi.lib().fmlp_proto_avg_f32(stacked.data_ptr(), K, C, D, rpc, cabi.f64_array(weight),
                                                  cabi.u64_array(masks), tmp.data_ptr(), cabi.stream_ptr(dev)),
                    "fmlp_proto_avg_f32")
-        out[:2 * n_listed] = tmp[:2 * n_listed]
+        out[:rpc * n_listed] = tmp[:rpc * n_listed]
     return out.cpu() if was_cpu else out
+
+
+def FedAvg_rela(Prototypes, weight, class_active_client_list):
+    """utils/FedAvg.py:95-103: like FedAvg_proto with ONE row per class ([C, D] inputs)."""
+    return FedAvg_proto(Prototypes, weight, class_active_client_list, _rows_per_class=1)
+
+
+def model_dist(w_1, w_2):
+    """sum over the float tensors, in key order, of ||w_1[k] - w_2[k]||_2 as a Python float
+    (reference utils/FedNoRo.py:106-115; utils/FedAvg.py:42-49 is the same loop without the int64
+    skip, which makes torch.norm raise on BatchNorm counters — the skip is kept here).
+    One deterministic multi-tensor launch pair instead of 2 x 727 tiny ops and 727 host syncs."""
+    if w_1.keys() != w_2.keys():
+        raise AssertionError("Error: cannot compute distance between dict with different keys")
+    first = next(iter(w_1.values()))
+    if not first.is_cuda:
+        if not torch.cuda.is_available():
+            raise cabi.FedMLPNativeError("model_dist needs a CUDA device (no CPU fallback)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        w_1 = OrderedDict((k, v.to(dev)) for k, v in w_1.items())
+        w_2 = OrderedDict((k, v.to(dev)) for k, v in w_2.items())
+    cabi.require_cuda(*w_1.values(), *w_2.values())
+    layout = layout_of(w_1)
+    if layout_of(w_2) is not layout:
+        raise ValueError("model_dist: the two state_dicts have different shapes / dtypes")
+    dev = next(iter(w_1.values())).device
+    plan = _multi_plan(layout, dev)
+    f_idx = plan["f_idx"]
+    T = len(f_idx)
+    v1, v2 = list(w_1.values()), list(w_2.values())
+    table = np.array([[v1[t].contiguous().data_ptr() for t in f_idx], [v2[t].contiguous().data_ptr() for t in f_idx]],
+                     dtype=np.int64).reshape(-1)
+    lib = cabi.lib()
+    with torch.cuda.device(dev):
+        table_dev = torch.from_numpy(table).to(dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = torch.empty(max(lib.fmlp_model_dist_ws_bytes(plan["n_chunks"], T), 256), dtype=torch.uint8, device=dev)
+        cabi.check(lib.fmlp_model_dist_f32(table_dev.data_ptr(), table_dev.data_ptr() + 8 * T, plan["numel"].data_ptr(),
+                                           plan["chunk_tensor"].data_ptr(), plan["chunk_start"].data_ptr(),
+                                           plan["tensor_chunk0"].data_ptr(), plan["n_chunks"], T, out.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), cabi.stream_ptr(dev)), "fmlp_model_dist_f32")
+        return float(out.item())
+
+
+def RSCFed(DMA, w_locals, K, dict_len, M):
+    """utils/FedAvg.py:25-40: per sub-sampled group, a plain average, distance-aware re-weighting
+    (exp(-0.01 * dist / n)) and a weighted average; then the plain average of the M group models."""
+    import math
+
+    w_sub = []
+    for group in DMA:
+        w_select = [w_locals[i] for i in group]
+        n_total = sum(dict_len[i] for i in group)
+        w_avg = Fed_w(w_select, [1] * K)
+        w = []
+        for i in group:
+            a = dict_len[i] / n_total
+            b = math.exp((-0.01) * (model_dist(w_locals[i], w_avg) / dict_len[i]))
+            w.append(a * b)
+        w_sub.append(Fed_w(w_select, w))
+    return Fed_w(w_sub, [1] * M)
+
+
+def DaAgg(w, dict_len, clean_clients, noisy_clients):
+    """utils/FedNoRo.py:84-103: distance-aware aggregation.  Noisy clients are down-weighted by
+    exp(-d / d_max), d = distance to the nearest clean client; the result is the weighted SUM with
+    the renormalised weights (no further division)."""
+    client_weight = np.array(dict_len)
+    client_weight = client_weight / client_weight.sum()
+    distance = np.zeros(len(dict_len))
+    for n_idx in noisy_clients:
+        distance[n_idx] = min(model_dist(w[n_idx], w[c_idx]) for c_idx in clean_clients)
+    distance = distance / distance.max()
+    client_weight = client_weight * np.exp(-distance)
+    client_weight = client_weight / client_weight.sum()
+    return FedAvg(w, [float(x) for x in client_weight], _divide=False)
 
 
 def FedAvg_tao(t, weight, class_active_client_list=None):

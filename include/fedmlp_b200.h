@@ -122,11 +122,25 @@ int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* weights, in
 
 /* Prototype aggregation, replaces utils/FedAvg.py:72-93 `FedAvg_proto`:
  *   out[2c+j] = (sum over clients i in act(c), in list order, of protos[i][2c+j]*n_i) / sum n_i
- * protos  device [K][2C][D] (stacked client prototypes);  weights host [K];
+ * protos  device [K][2C][D] (stacked client prototypes);  weights host [K] (double);
  * class_clients  host [C] bit masks over clients (bit i set = client i annotates class c),
  *                K <= 64.  Empty act(c) gives 0/0 = NaN exactly like the reference.        */
-int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, const double* weights,
-                       const uint64_t* class_clients, float* out, fmlp_stream_t stream);
+int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, int rows_per_class,
+                       const double* weights, const uint64_t* class_clients, float* out,
+                       fmlp_stream_t stream);
+/* rows_per_class = 2: the layout above (FedAvg_proto).  rows_per_class = 1: protos [K][C][D], one row
+ * per class = utils/FedAvg.py:95-103 `FedAvg_rela`.                                            */
+
+/* Model distance, replaces utils/FedNoRo.py:106-115 / utils/FedAvg.py:42-49 `model_dist`:
+ *   out[0] = sum over the T float tensors, in table order, of || a_t - b_t ||_2
+ * (int64 tensors are skipped by the caller, as FedNoRo.py:110-111 does).  Tables as in
+ * fmlp_fedavg_multi_f32 plus tensor_chunk0_dev [T+1] = index of every tensor's first chunk.   */
+size_t fmlp_model_dist_ws_bytes(int64_t n_chunks, int T);
+int fmlp_model_dist_f32(const float* const* a_table_dev, const float* const* b_table_dev,
+                        const int64_t* numel_dev, const int32_t* chunk_tensor_dev,
+                        const int64_t* chunk_start_dev, const int64_t* tensor_chunk0_dev,
+                        int64_t n_chunks, int T, float* out, void* ws, size_t ws_bytes,
+                        fmlp_stream_t stream);
 
 /* ------------------------------------------------------------------ K2: class prototypes
  * Replaces utils/local_training.py:973-1000 (stage 1) and :1208-1249 (stage 2):

@@ -79,6 +79,63 @@ def fedavg_tao(t, weight, class_client_list=None):
     return avg
 
 
+# ------------------------------------------------------------------------------------ §8f.3 other aggregators
+def fedavg_rela(prototypes, weight, class_active_client_list):
+    """utils/FedAvg.py:95-103: FedAvg_proto with one row per class."""
+    avg = torch.zeros((len(prototypes[0]), len(prototypes[0][0])))
+    w_arr = np.array(weight)
+    for cls, clients in enumerate(class_active_client_list):
+        acc = torch.zeros_like(prototypes[0][0])
+        for cid in clients:
+            acc = prototypes[cid][cls] * weight[cid] + acc
+        avg[cls] = acc / np.sum(w_arr[clients])
+    return avg
+
+
+def model_dist(w_1, w_2):
+    """utils/FedNoRo.py:106-115: per-key L2 norms of the difference (int tensors skipped), added in
+    key order in fp32; returned as a Python float."""
+    assert w_1.keys() == w_2.keys()
+    total = torch.zeros(1).float()
+    for key in w_1.keys():
+        if "int" in str(w_1[key].dtype):
+            continue
+        total += torch.norm(w_1[key] - w_2[key])
+    return total.item()
+
+
+def rscfed(dma, w_locals, k, dict_len, m):
+    """utils/FedAvg.py:25-40."""
+    import math
+    w_sub = []
+    for group in dma:
+        sel = [w_locals[i] for i in group]
+        n_total = sum(dict_len[i] for i in group)
+        w_avg = fedavg(sel, [1] * k)
+        ws = [(dict_len[i] / n_total) * math.exp(-0.01 * (model_dist(w_locals[i], w_avg) / dict_len[i])) for i in group]
+        w_sub.append(fedavg(sel, ws))
+    return fedavg(w_sub, [1] * m)
+
+
+def daagg(w, dict_len, clean_clients, noisy_clients):
+    """utils/FedNoRo.py:84-103."""
+    cw = np.array(dict_len)
+    cw = cw / cw.sum()
+    distance = np.zeros(len(dict_len))
+    for n_idx in noisy_clients:
+        distance[n_idx] = min(model_dist(w[n_idx], w[c_idx]) for c_idx in clean_clients)
+    distance = distance / distance.max()
+    cw = cw * np.exp(-distance)
+    cw = cw / cw.sum()
+    out = OrderedDict()
+    for key, first in w[0].items():
+        acc = first * cw[0]
+        for i in range(1, len(w)):
+            acc = acc + w[i][key] * cw[i]
+        out[key] = acc
+    return out
+
+
 # ------------------------------------------------------------------------------------ a6
 def cosine_similarity_fast(x1, x2):
     """utils/local_training.py:1417-1435 CosineSimilarityFast.forward: x1 [N,D], x2 [1,D] ->

@@ -6,6 +6,7 @@ The reference (szbonaldo/FedMLP, mounted read-only at /root/reference) has no te
 golden vectors, so the fixtures are outputs of its own code on small seeded inputs:
 
   fedavg.npz      utils/FedAvg.py  FedAvg / FedAvg_proto / FedAvg_tao, called directly
+  aggregators.npz utils/FedAvg.py RSCFed / model_dist / FedAvg_rela, utils/FedNoRo.py DaAgg / model_dist
   tagging.npz     utils/local_training.py CosineSimilarityFast + utils/utils.py
                   max_m_indices / min_n_indices (incl. ties), called directly
   maskfill.npz    utils/local_training.py DatasetSplit_pseudo.__getitem__, called directly
@@ -94,6 +95,56 @@ def make_fedavg(ref):
     out["tao/out_lists"] = ref.FedAvg.FedAvg_tao(taos, weight, neg_lists)
     out["tao/out_plain"] = ref.FedAvg.FedAvg_tao(taos, weight)
     np.savez_compressed(GOLDEN_DIR / "fedavg.npz", **out)
+
+
+# ----------------------------------------------------------------------------------- other aggregators
+def make_aggregators(ref):
+    """utils/FedAvg.py RSCFed / model_dist / FedAvg_rela and utils/FedNoRo.py DaAgg / model_dist."""
+    from collections import OrderedDict
+    g = torch.Generator().manual_seed(77)
+    shapes = [("conv.weight", (6, 3, 3, 3)), ("bn.weight", (6,)), ("bn.running_var", (6,)),
+              ("bn.num_batches_tracked", ()), ("fc.weight", (5, 2500)), ("fc.bias", (5,))]
+    K = 6
+    base = {n: torch.randn(s, generator=g) for n, s in shapes if "num_batches" not in n}
+    clients = []
+    for k in range(K):
+        sd = OrderedDict()
+        for n, s in shapes:
+            sd[n] = torch.tensor(50 + k, dtype=torch.int64) if "num_batches" in n else base[n] + 0.05 * torch.randn(s, generator=g)
+        clients.append(sd)
+    out = {"names": np.array([n for n, _ in shapes])}
+    for k, sd in enumerate(clients):
+        for n in sd:
+            out[f"in/{k}/{n}"] = _np(sd[n])
+    dict_len = [5000, 4000, 6000, 3000, 5500, 4500]
+    out["dict_len"] = np.array(dict_len)
+    # model_dist (FedNoRo version skips int tensors)
+    out["model_dist/0_1"] = np.array(ref.FedNoRo.model_dist(clients[0], clients[1]))
+    out["model_dist/2_5"] = np.array(ref.FedNoRo.model_dist(clients[2], clients[5]))
+    # DaAgg
+    clean, noisy = [0, 2, 3], [1, 4, 5]
+    res = ref.FedNoRo.DaAgg(clients, dict_len, clean, noisy)
+    out["daagg/clean"], out["daagg/noisy"] = np.array(clean), np.array(noisy)
+    for n in res:
+        out[f"daagg/out/{n}"] = _np(res[n])
+        out[f"daagg/dtype/{n}"] = np.array(str(res[n].dtype))
+    # RSCFed works on float-only dicts in the reference (its model_dist calls torch.norm on every key)
+    fclients = [OrderedDict((n, v) for n, v in sd.items() if v.dtype == torch.float32) for sd in clients]
+    DMA = [[0, 1, 2], [3, 4, 5], [1, 3, 5], [0, 2, 4]]
+    res = ref.FedAvg.RSCFed(DMA, fclients, 3, dict_len, 4)
+    out["rscfed/dma"] = np.array(DMA)
+    out["rscfed/model_dist_0_1"] = np.array(ref.FedAvg.model_dist(fclients[0], fclients[1]))
+    for n in res:
+        out[f"rscfed/out/{n}"] = _np(res[n])
+    # FedAvg_rela
+    C, D = 5, 24
+    protos = [torch.randn(C, D, generator=g) for _ in range(K)]
+    lists = [[0, 3], [1], [2, 4, 5], [], [0, 1, 2, 3, 4, 5]]
+    out["rela/in"] = np.stack([_np(p) for p in protos])
+    out["rela/lists"] = np.array([",".join(map(str, l)) for l in lists])
+    with np.errstate(all="ignore"):
+        out["rela/out"] = _np(ref.FedAvg.FedAvg_rela(protos, dict_len, lists))
+    np.savez_compressed(GOLDEN_DIR / "aggregators.npz", **out)
 
 
 # ----------------------------------------------------------------------------------- tagging
@@ -384,6 +435,7 @@ def main():
     ref = ref_loader.load()
     torch.set_num_threads(1)   # fixed reduction order for the recorded sums
     make_fedavg(ref)
+    make_aggregators(ref)
     make_tagging(ref)
     make_maskfill(ref)
     make_flow(ref)

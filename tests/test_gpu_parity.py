@@ -516,3 +516,39 @@ def test_golden_flow_tagging_and_prototypes(F, mode):
         res = F.build_prototypes(cuda(pfeat), cuda(plab), cuda(plogit), act, neg, L, U, guard_empty=True)
         np.testing.assert_allclose(res.proto[0].cpu().numpy(), flow[f"s2_{r}/proto"], rtol=1e-5, atol=1e-6)
         np.testing.assert_array_equal(res.t()[0], flow[f"s2_{r}/t"])
+
+
+# =============================================================================== other aggregators (§8f.3)
+def test_other_aggregators_golden(F):
+    """model_dist / DaAgg / RSCFed / FedAvg_rela through the kernels vs the reference's own outputs."""
+    z = gu.load("aggregators.npz")
+    names = [str(n) for n in z["names"]]
+    clients = [OrderedDict((n, cuda(z[f"in/{k}/{n}"].copy())) for n in names) for k in range(6)]
+    dict_len = z["dict_len"].tolist()
+    for a, b in ((0, 1), (2, 5)):
+        ref = float(z[f"model_dist/{a}_{b}"])
+        assert abs(F.model_dist(clients[a], clients[b]) - ref) <= 1e-5 * ref
+        flat_a, flat_b = F.FlatStateDict.from_state_dict(clients[a]), F.FlatStateDict.from_state_dict(clients[b])
+        assert abs(F.model_dist(flat_a, flat_b) - ref) <= 1e-5 * ref
+    res = F.DaAgg(clients, dict_len, z["daagg/clean"].tolist(), z["daagg/noisy"].tolist())
+    for n in names:
+        assert res[n].dtype == torch.float32
+        np.testing.assert_allclose(res[n].cpu().numpy(), z[f"daagg/out/{n}"], rtol=1e-5, atol=1e-6)
+    fclients = [OrderedDict((n, v) for n, v in sd.items() if v.dtype == torch.float32) for sd in clients]
+    res = F.RSCFed(z["rscfed/dma"].tolist(), fclients, 3, dict_len, 4)
+    for n in res:
+        np.testing.assert_allclose(res[n].cpu().numpy(), z[f"rscfed/out/{n}"], rtol=1e-5, atol=1e-6)
+    protos = [cuda(p.copy()) for p in z["rela/in"]]
+    out = F.FedAvg_rela(protos, dict_len, gu.parse_lists(z["rela/lists"]))
+    np.testing.assert_array_equal(out.cpu().numpy(), z["rela/out"])
+
+
+def test_model_dist_densenet_sized(F):
+    from fedmlp_b200.shapes import densenet121_state_shapes, synth_state_dict
+    shapes = densenet121_state_shapes(5)
+    a = synth_state_dict(shapes, 1)
+    b = synth_state_dict(shapes, 2)
+    ref = O.model_dist(a, b)
+    got = F.model_dist(OrderedDict((k, v.to(DEV)) for k, v in a.items()), OrderedDict((k, v.to(DEV)) for k, v in b.items()))
+    assert abs(got - ref) <= 1e-5 * ref
+    assert abs(F.model_dist(a, b) - ref) <= 1e-5 * ref          # CPU dicts are staged to the GPU

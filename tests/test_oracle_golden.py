@@ -189,3 +189,29 @@ def test_flow_tagging_state_across_rounds(flow):
     state.step(torch.from_numpy(feat1[perm]), proto, cf, nf, python_sort=True)
     for j in range(2 * len(neg)):
         assert state.traindata_idx[j] == [int(v) for v in flow[f"s2_1/traindata_idx/{j}"]]
+
+
+# ------------------------------------------------------------------------------------ other aggregators (§8f.3)
+def _agg_inputs(z):
+    names = [str(n) for n in z["names"]]
+    return names, [OrderedDict((n, torch.from_numpy(z[f"in/{k}/{n}"].copy())) for n in names) for k in range(6)]
+
+
+def test_other_aggregators_match_reference():
+    z = gu.load("aggregators.npz")
+    names, clients = _agg_inputs(z)
+    dict_len = z["dict_len"].tolist()
+    assert abs(O.model_dist(clients[0], clients[1]) - float(z["model_dist/0_1"])) <= 1e-6 * float(z["model_dist/0_1"])
+    assert abs(O.model_dist(clients[2], clients[5]) - float(z["model_dist/2_5"])) <= 1e-6 * float(z["model_dist/2_5"])
+    res = O.daagg(clients, dict_len, z["daagg/clean"].tolist(), z["daagg/noisy"].tolist())
+    for n in names:
+        assert str(res[n].dtype) == str(z[f"daagg/dtype/{n}"])
+        np.testing.assert_allclose(res[n].numpy(), z[f"daagg/out/{n}"], rtol=1e-6, atol=1e-7)
+    fclients = [OrderedDict((n, v) for n, v in sd.items() if v.dtype == torch.float32) for sd in clients]
+    res = O.rscfed(z["rscfed/dma"].tolist(), fclients, 3, dict_len, 4)
+    for n in res:
+        np.testing.assert_allclose(res[n].numpy(), z[f"rscfed/out/{n}"], rtol=1e-6, atol=1e-7)
+    protos = [torch.from_numpy(p.copy()) for p in z["rela/in"]]
+    with np.errstate(all="ignore"):
+        out = O.fedavg_rela(protos, dict_len, gu.parse_lists(z["rela/lists"]))
+    np.testing.assert_array_equal(out.numpy(), z["rela/out"])
