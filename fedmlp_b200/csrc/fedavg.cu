@@ -291,6 +291,33 @@ __global__ void __launch_bounds__(256) proto_avg_kernel(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------- tao aggregation (float64)
+struct TaoAvgArgs {
+    const double* t;   // [K][C]
+    double* out;       // [C]
+    double w[FMLP_MAX_CLIENTS];
+    uint64_t class_clients[FMLP_MAX_CLASSES];
+    int K, C, use_lists;
+};
+
+// utils/FedAvg.py:51-70 in the reference's operation order, in IEEE double without contraction:
+//   lists given : t_avg[c] = (sum_{i in list(c), ascending} t_i[c]*w_i) / (sum w_i), 1.0 for an empty list
+//   no lists    : t_avg    = (sum_i t_i*w_i) / sum(w)   (the divisor is passed in w[K])
+__global__ void tao_avg_kernel(const __grid_constant__ TaoAvgArgs a, double total_w) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    double acc = 0.0, wsum = 0.0;
+    bool any = false;
+    for (int i = 0; i < a.K; ++i) {
+        if (a.use_lists && !((a.class_clients[c] >> i) & 1ull)) continue;
+        acc = __dadd_rn(acc, __dmul_rn(a.t[(int64_t)i * a.C + c], a.w[i]));
+        wsum = __dadd_rn(wsum, a.w[i]);
+        any = true;
+    }
+    if (a.use_lists) a.out[c] = any ? __ddiv_rn(acc, wsum) : 1.0;
+    else a.out[c] = __ddiv_rn(acc, total_w);
+}
+
 // ---------------------------------------------------------------- model_dist
 // utils/FedNoRo.py:106-115 (and utils/FedAvg.py:42-49): sum over the float tensors, in key order,
 // of ||w1[k] - w2[k]||_2.  Deterministic: per-chunk sums of squares (fixed tree inside the CTA),
@@ -492,5 +519,17 @@ extern "C" int fmlp_model_dist_f32(const float* const* a_table_dev, const float*
         if (rc != FMLP_OK) return rc;
     }
     model_dist_finalize_kernel<<<1, 256, 0, st>>>(a);
+    return launch_status();
+}
+
+extern "C" int fmlp_tao_avg_f64(const double* t_dev, int K, int C, const double* weights,
+                                const uint64_t* class_clients, double total_weight, double* out_dev,
+                                fmlp_stream_t stream) {
+    if (!t_dev || !weights || !out_dev || C < 1 || C > FMLP_MAX_CLASSES || check_k(K) != FMLP_OK) return FMLP_ERR_BAD_ARG;
+    TaoAvgArgs a;
+    a.t = t_dev; a.out = out_dev; a.K = K; a.C = C; a.use_lists = class_clients ? 1 : 0;
+    for (int i = 0; i < FMLP_MAX_CLIENTS; ++i) a.w[i] = i < K ? weights[i] : 0.0;
+    for (int c = 0; c < FMLP_MAX_CLASSES; ++c) a.class_clients[c] = (class_clients && c < C) ? class_clients[c] : 0ull;
+    tao_avg_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, total_weight);
     return launch_status();
 }

@@ -45,11 +45,20 @@ struct SimArgs {
 template <int NPAIR, bool FOLD>
 struct SimCfg {
     static constexpr int NV = FOLD ? NPAIR : 2 * NPAIR;
-    static constexpr int R = (NV <= 16) ? 4 : 2;            // rows per warp tile
+    // rows per warp tile / threads per CTA: accumulators cost 2*R*(NV+1) registers, and the kernel
+    // needs >= 12 warps per SM to hide FFMA2 / LDS latency (r01 ncu at C=14: 4 rows x 14 vectors
+    // = 192 registers -> 8 warps -> 38 % issue utilisation), so R shrinks as NV grows.
+#ifndef FMLP_SIM_R_MID
+#define FMLP_SIM_R_MID 3
+#endif
+#ifndef FMLP_SIM_THREADS_MID
+#define FMLP_SIM_THREADS_MID 384
+#endif
+    static constexpr int R = (NV <= 10) ? 4 : (NV <= 16 ? FMLP_SIM_R_MID : 2);
 #ifndef FMLP_SIM_THREADS_SMALL
 #define FMLP_SIM_THREADS_SMALL 384
 #endif
-    static constexpr int THREADS = (NV <= 10) ? FMLP_SIM_THREADS_SMALL : 256;  // register caps 168 (384 thr) / 255
+    static constexpr int THREADS = (NV <= 10) ? FMLP_SIM_THREADS_SMALL : (NV <= 16 ? FMLP_SIM_THREADS_MID : 256);
     static constexpr int V = R * (NV + 1);                  // values reduced per tile
     static constexpr int SCRATCH = (V + 3) & ~3;
 #ifndef FMLP_SIM_DEPTH
@@ -231,15 +240,29 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
             for (int r = 0; r < R; ++r) lds_pairs(ring_addr + slot + r * 512, f0[r], f1[r]);
             slot = (slot + R * 512 == DEPTH * R * 512) ? 0u : slot + R * 512;
             const uint32_t base = sP_addr + (uint32_t)c * (NV * 512u);
+            // two prototype vectors per step and the f0 products of all of them before any f1
+            // product: the two FFMA2 that hit the same accumulator are 2R-1 independent FFMA2 apart
+            // (back to back they stalled on the 4-cycle FMA latency: "wait" was the top stall reason)
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                u64 p0, p1;
+            for (int j = 0; j < NV; j += 2) {
+                u64 p0, p1, q0 = 0ull, q1 = 0ull;
                 lds_pairs(base + j * 512, p0, p1);
+                if (j + 1 < NV) lds_pairs(base + (j + 1) * 512, q0, q1);
 #pragma unroll
-                for (int r = 0; r < R; ++r) { fma2(acc[r][j], f0[r], p0); fma2(acc[r][j], f1[r], p1); }
+                for (int r = 0; r < R; ++r) {
+                    fma2(acc[r][j], f0[r], p0);
+                    if (j + 1 < NV) fma2(acc[r][j + 1], f0[r], q0);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    fma2(acc[r][j], f1[r], p1);
+                    if (j + 1 < NV) fma2(acc[r][j + 1], f1[r], q1);
+                }
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) { fma2(nrm[r], f0[r], f0[r]); fma2(nrm[r], f1[r], f1[r]); }
+            for (int r = 0; r < R; ++r) fma2(nrm[r], f0[r], f0[r]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) fma2(nrm[r], f1[r], f1[r]);
         }
 
         // ---- combine the 32 lane partials (transposed reduction) ------------------------

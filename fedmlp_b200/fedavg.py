@@ -355,20 +355,26 @@ def DaAgg(w, dict_len, clean_clients, noisy_clients):
 
 def FedAvg_tao(t, weight, class_active_client_list=None):
     """Per-class weighted mean of the clients' difficulty statistics t (reference
-    utils/FedAvg.py:51-70).  K x C float64 scalars on the host, exactly like the reference:
-    this is host-side bookkeeping (the values are only printed by the tagger,
-    local_training.py:1068), not a device kernel."""
-    n = len(t[0])
-    avg = np.zeros(n, dtype=np.float64)
-    if class_active_client_list is None:
-        for i, tao in enumerate(t):
-            avg += np.asarray(tao, dtype=np.float64) * float(weight[i])
-        return avg / float(sum(weight))
-    for cls, clients in enumerate(class_active_client_list):
-        wsum = 0.0
-        for i, tao in enumerate(t):
-            if i in clients:
-                avg[cls] += tao[cls] * float(weight[i])
-                wsum += float(weight[i])
-        avg[cls] = 1.0 if len(clients) == 0 else avg[cls] / wsum
-    return avg
+    utils/FedAvg.py:51-70).  t: K float64 arrays [C]; returns a float64 numpy [C] like the
+    reference.  K*C doubles go through fmlp_tao_avg_f64 (IEEE double, the reference's operation
+    order -> bit-identical); main.py:223 passes the per-class lists of clients that MISS the class."""
+    K, n = len(t), len(t[0])
+    if K > cabi.MAX_CLIENTS:
+        raise NotImplementedError("FedAvg_tao supports at most 64 clients per call")
+    if not torch.cuda.is_available():
+        raise cabi.FedMLPNativeError("FedAvg_tao needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t_dev = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.float64) for x in t]))).to(dev)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    masks = None
+    if class_active_client_list is not None:
+        m = [0] * n
+        for cls, clients in enumerate(class_active_client_list):
+            for cid in clients:
+                if 0 <= int(cid) < K:
+                    m[cls] |= 1 << int(cid)
+        masks = cabi.u64_array(m)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().fmlp_tao_avg_f64(t_dev.data_ptr(), K, n, cabi.f64_array([float(x) for x in weight[:K]]), masks,
+                                               float(sum(weight)), out.data_ptr(), cabi.stream_ptr(dev)), "fmlp_tao_avg_f64")
+    return out.cpu().numpy()

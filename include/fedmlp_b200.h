@@ -131,6 +131,15 @@ int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, int rows_per_cl
 /* rows_per_class = 2: the layout above (FedAvg_proto).  rows_per_class = 1: protos [K][C][D], one row
  * per class = utils/FedAvg.py:95-103 `FedAvg_rela`.                                            */
 
+/* Difficulty aggregation, replaces utils/FedAvg.py:51-70 `FedAvg_tao` (float64, bit-identical:
+ * same operation order, IEEE double mul/add/div):
+ *   class_clients != NULL: out[c] = sum_{i in list(c)} t[i][c]*w_i / sum w_i, 1.0 for an empty list
+ *   class_clients == NULL: out[c] = sum_i t[i][c]*w_i / total_weight
+ * t_dev device [K][C] double; weights host [K]; out_dev device [C] double.                     */
+int fmlp_tao_avg_f64(const double* t_dev, int K, int C, const double* weights,
+                     const uint64_t* class_clients, double total_weight, double* out_dev,
+                     fmlp_stream_t stream);
+
 /* Model distance, replaces utils/FedNoRo.py:106-115 / utils/FedAvg.py:42-49 `model_dist`:
  *   out[0] = sum over the T float tensors, in table order, of || a_t - b_t ||_2
  * (int64 tensors are skipped by the caller, as FedNoRo.py:110-111 does).  Tables as in

@@ -82,7 +82,8 @@ def test_flat_layout_and_densenet_shapes():
     assert not torch.equal(clone["classifier.bias"], flat["classifier.bias"])
 
 
-def test_fedavg_tao_host_path_matches_oracle():
+@pytest.mark.gpu
+def test_fedavg_tao_matches_oracle_bitwise():
     import numpy as np
     import fedmlp_b200 as F
     from oracle import fedmlp_oracle as O

@@ -142,6 +142,35 @@ __global__ void k_mode2(const float* __restrict__ f, long n, int D, float* out) 
     }
     if (acc == 123.456f) out[0] = acc;
 }
+// mode 5: CTA-per-rows like mode 2, but row blocks are INTERLEAVED over the CTAs (CTA b takes
+// blocks b, b+G, ...), so the whole chip sweeps one linear front (the FedAvg access shape)
+template <int U>
+__global__ void k_mode5(const float* __restrict__ f, long n, int D, float* out) {
+    const int col = threadIdx.x * 4;
+    float acc = 0.f;
+    for (long r = (long)blockIdx.x * U; r < n; r += (long)gridDim.x * U) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (r + u < n) ? ldg(f + (r + u) * (long)D + col) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += a[u].x + a[u].y + a[u].z + a[u].w;
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+// mode 6: flat grid-stride float4 read (the fedavg_flat shape with K = 1 array)
+template <int U>
+__global__ void k_mode6(const float* __restrict__ f, long nvec, float* out) {
+    float acc = 0.f;
+    const long nt = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += nt * U) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (v + u * nt < nvec) ? ldg(f + (v + u * nt) * 4) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += a[u].x + a[u].y + a[u].z + a[u].w;
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
 template <typename F> float timeit(F launch, float* flush, size_t flush_n) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     std::vector<float> ts;
@@ -184,6 +213,12 @@ int main() {
     rep("mode1 4 chunks/row 12 warps x1", timeit([&] { k_mode1<4><<<sms, 384>>>(f, n, D, out); }, flush, fb));
     rep("mode1 8 chunks/row 12 warps x1", timeit([&] { k_mode1<8><<<sms, 384>>>(f, n, D, out); }, flush, fb));
     rep("mode1 8 chunks/row 8 warps x4", timeit([&] { k_mode1<8><<<sms * 4, 256>>>(f, n, D, out); }, flush, fb));
+    rep("mode5 interleaved U=4 256thr x8 CTA/SM", timeit([&] { k_mode5<4><<<sms * 8, 256>>>(f, n, D, out); }, flush, fb));
+    rep("mode5 interleaved U=8 256thr x4 CTA/SM", timeit([&] { k_mode5<8><<<sms * 4, 256>>>(f, n, D, out); }, flush, fb));
+    rep("mode5 interleaved U=8 256thr x8 CTA/SM", timeit([&] { k_mode5<8><<<sms * 8, 256>>>(f, n, D, out); }, flush, fb));
+    rep("mode6 flat grid-stride U=8 256thr x4 CTA/SM", timeit([&] { k_mode6<8><<<sms * 4, 256>>>(f, n * D / 4, out); }, flush, fb));
+    rep("mode6 flat grid-stride U=8 256thr x8 CTA/SM", timeit([&] { k_mode6<8><<<sms * 8, 256>>>(f, n * D / 4, out); }, flush, fb));
+    rep("mode6 flat grid-stride U=4 256thr x8 CTA/SM", timeit([&] { k_mode6<4><<<sms * 8, 256>>>(f, n * D / 4, out); }, flush, fb));
     rep("mode2 U=8 256thr x2 CTA/SM", timeit([&] { k_mode2<8><<<sms * 2, 256>>>(f, n, D, out); }, flush, fb));
     rep("mode2 U=8 256thr x4 CTA/SM", timeit([&] { k_mode2<8><<<sms * 4, 256>>>(f, n, D, out); }, flush, fb));
     rep("mode2 U=4 256thr x8 CTA/SM", timeit([&] { k_mode2<4><<<sms * 8, 256>>>(f, n, D, out); }, flush, fb));
