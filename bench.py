@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--proto-on-side", type=int, default=1,
+                    help="N>1: 1 = prototypes share the side stream with the aggregation, 0 = stay on the main chain")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused fold+all-reduce kernel over peer memory, or local fold + NCCL all-reduce")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
@@ -336,11 +338,11 @@ def gpu_arm(a):
         if fused is not None:
             return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
                                         inp["feat_proto"], inp["logits_proto"], inp["flats"], w_norm, timers=timers,
-                                        fedavg_out=fed_out, divide=False, side_stream=side,
+                                        fedavg_out=fed_out, divide=False, side_stream=side, proto_on_side=a.proto_on_side,
                                         aggregate_fn=lambda bufs, w: fused(bufs, w))
         return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
                                     inp["feat_proto"], inp["logits_proto"], inp["flats"], w_norm, timers=timers,
-                                    fedavg_out=fed_out, divide=False, side_stream=side,
+                                    fedavg_out=fed_out, divide=False, side_stream=side, proto_on_side=a.proto_on_side,
                                     after_aggregate=lambda g: dist.all_reduce(g))
 
     def fence():

@@ -109,7 +109,7 @@ class ClientShard:
 
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
-                       side_stream=None, after_aggregate=None, aggregate_fn=None) -> RoundResult:
+                       side_stream=None, after_aggregate=None, aggregate_fn=None, proto_on_side=True) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
@@ -125,7 +125,9 @@ class ClientShard:
         after_aggregate(glob): called with the FedAvg stream current right after the FedAvg launch —
         the multi-GPU driver issues its all-reduce there.  The main stream joins before returning.
         aggregate_fn(client_flats, weights) -> [P] tensor: replaces the FedAvg launch altogether (the
-        fused fold + all-reduce kernel of dist.FusedFedAvgAllReduce)."""
+        fused fold + all-reduce kernel of dist.FusedFedAvgAllReduce).
+        proto_on_side=False keeps the prototype pass on the main stream (multi-GPU: the aggregation
+        with its NVLink-bound phases is then the whole side chain and overlaps HBM-bound work)."""
         N, C, S = self.N, self.C, self.S
         D = feat_tag.shape[1]
         if (tuple(feat_tag.shape) != (N, D) or tuple(feat_proto.shape) != (N, D) or tuple(labels.shape) != (N, C)
@@ -156,7 +158,7 @@ class ClientShard:
 
             out = {"glob": glob}
 
-            def chain_b(stream_b):
+            def proto_stage(stream_b):
                 sb = stream_b.cuda_stream
                 check(lib.fmlp_proto_build_f32(feat_proto.data_ptr(), D, D, labels.data_ptr(), logits_proto.data_ptr(), 0,
                                                C, S, pl.rows, pl.active, pl.missing, self.L, self.U, 1,
@@ -164,6 +166,9 @@ class ClientShard:
                                                pl.ws_proto.data_ptr(), pl.ws_proto.numel(), sb), "fmlp_proto_build_f32")
                 if stream_b is stream:
                     mark("proto")
+
+            def aggregate_stage(stream_b):
+                sb = stream_b.cuda_stream
                 if aggregate_fn is not None:
                     out["glob"] = aggregate_fn(client_flats, weights)
                 else:
@@ -180,7 +185,9 @@ class ClientShard:
             if side_stream is not None:
                 side_stream.wait_stream(stream)
                 with torch.cuda.stream(side_stream):
-                    chain_b(side_stream)
+                    if proto_on_side:
+                        proto_stage(side_stream)
+                    aggregate_stage(side_stream)
             check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
                                        tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], st), "fmlp_tag_sim_f32")
             mark("sim")
@@ -198,9 +205,12 @@ class ClientShard:
                                                pl.ws_loss.data_ptr(), pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
             mark("loss")
             if side_stream is not None:
+                if not proto_on_side:
+                    proto_stage(stream)
                 stream.wait_stream(side_stream)
             else:
-                chain_b(stream)
+                proto_stage(stream)
+                aggregate_stage(stream)
         if self.keep_history:
             # keep the lazily materialised host lists of the tagger in sync with this round's picks
             tg._history.append((pl.counts.clone(), pl.sel.clone(), pl.cap))
