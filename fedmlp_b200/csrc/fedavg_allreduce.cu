@@ -24,6 +24,8 @@
 // peer pointers.  Weights arrive pre-normalised (n_k / sum n), so no divide pass is needed.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -164,6 +166,9 @@ extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* 
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fedavg_allreduce_kernel, kArThreads, 0);
         if (e != cudaSuccess) return (int)e;
         per_sm = b < 1 ? 1 : (b > 4 ? 4 : b);
+        // tuning knob: a smaller footprint leaves SM resources to the concurrent tagging/prototype
+        // kernels during the NVLink-bound phases
+        if (const char* e = getenv("FMLP_AR_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
     }
     int64_t blocks = ((int64_t)world * (slice_len >> 2) + kArThreads - 1) / kArThreads;
     if (blocks > (int64_t)sms * per_sm) blocks = (int64_t)sms * per_sm;

@@ -152,7 +152,10 @@ class ClientShard:
 
             def mark(name):
                 if timers is not None:
-                    e = torch.cuda.Event(enable_timing=True)
+                    # timers="external": events that become record nodes when the round is captured
+                    # in a CUDA graph (per-stage timing without eager launch gaps)
+                    e = (torch.cuda.Event(enable_timing=True, external=True) if timers == "external"
+                         else torch.cuda.Event(enable_timing=True))
                     e.record(stream)
                     ev[name] = e
 
