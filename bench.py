@@ -71,7 +71,6 @@ def make_device_inputs(a, rank, dev):
     """Seeded synthetic inputs of the named shapes, created on the device (setup, untimed)."""
     import torch
     from fedmlp_b200.shapes import count_params, densenet121_state_shapes
-    from fedmlp_b200.flat import layout_of
 
     S, n, C, D = a.clients_per_gpu, a.rows_per_client, a.classes, a.dim
     N = S * n
@@ -287,7 +286,6 @@ def gpu_arm(a):
     import torch
     import torch.distributed as dist
 
-    import fedmlp_b200 as F
     from fedmlp_b200 import _cabi as cabi
     from fedmlp_b200.round import ClientShard
 

@@ -50,22 +50,6 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
                  : "l"(p));
     return v;
 }
-// 256-bit form (sm_100+): one request covers 32 B per lane; the only form that accepts the
-// L2::evict_first hint.  Requires 32-byte alignment.
-struct float8 { float4 lo, hi; };
-__device__ __forceinline__ float8 ld_stream_f8(const float* p) {
-    float8 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.lo.z), "=f"(v.lo.w), "=f"(v.hi.x),
-                   "=f"(v.hi.y), "=f"(v.hi.z), "=f"(v.hi.w)
-                 : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_stream_f1(const float* p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
                  "f"(v.y), "f"(v.z), "f"(v.w)

@@ -53,8 +53,6 @@ __device__ __forceinline__ void fold_clients(float4& acc, int first, int K, cons
     }
 }
 
-__device__ __forceinline__ float fold_scalar_init(float s, float w) { return __fmul_rn(s, w); }
-
 template <bool kVec>
 __global__ void __launch_bounds__(kFedAvgThreads, 4)
 fedavg_flat_kernel(const __grid_constant__ FedAvgArgs a) {

@@ -20,8 +20,6 @@ backend in tests (the CUDA kernel is the default and the only product path).
 """
 from __future__ import annotations
 
-from collections import OrderedDict
-
 import numpy as np
 import torch
 import torch.distributed as dist

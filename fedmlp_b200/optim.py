@@ -1,0 +1,60 @@
+"""Fused Adam on a flat client model (kernel adam.cu).
+
+`FlatAdam(module)` flattens the module's parameters / buffers into one fp32 buffer
+(`flat.flatten_module_`), keeps the gradients and both Adam moments in flat buffers of the same
+layout, and performs `step()` (+ optional `zero_grad`) as ONE kernel launch instead of ~10 foreach
+kernels over 364 tensors.  Same hyper-parameters and arithmetic as the optimizer the reference
+creates every round: torch.optim.Adam(net.parameters(), lr, betas=(0.9, 0.999), weight_decay=5e-4)
+(utils/local_training.py:912-913, :1149-1150).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi as cabi
+from .flat import FlatStateDict, flatten_module_
+
+_CHUNK = cabi.FEDAVG_CHUNK
+
+
+class FlatAdam:
+    def __init__(self, module: torch.nn.Module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 flat: FlatStateDict | None = None):
+        self.module = module
+        self.flat = flat if flat is not None else flatten_module_(module)
+        buf = self.flat.flat_f32
+        cabi.require_cuda(buf)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.grad = torch.zeros_like(buf)
+        self.exp_avg = torch.zeros_like(buf)
+        self.exp_avg_sq = torch.zeros_like(buf)
+        self.step_count = 0
+        lay = self.flat.layout
+        offset_of = {k: (lay.offsets[i], lay.numels[i]) for i, k in enumerate(lay.keys) if not lay.is_int[i]}
+        starts, lens = [], []
+        for name, p in module.named_parameters():
+            off, n = offset_of[name]
+            if p.data_ptr() != buf.data_ptr() + 4 * off:
+                raise ValueError(f"parameter {name} is not a view of the flat buffer")
+            p.grad = self.grad[off:off + n].view_as(p)       # autograd accumulates in place from now on
+            for s in range(0, n, _CHUNK):
+                starts.append(off + s)
+                lens.append(min(_CHUNK, n - s))
+        dev = buf.device
+        self.chunk_start = torch.tensor(starts, dtype=torch.int64, device=dev)
+        self.chunk_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+        self.n_chunks = len(starts)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self, zero_grad=False):
+        """One Adam step; zero_grad=True also clears the gradients in the same launch."""
+        self.step_count += 1
+        buf = self.flat.flat_f32
+        with torch.cuda.device(buf.device):
+            cabi.check(cabi.lib().fmlp_adam_step_f32(
+                buf.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self.chunk_start.data_ptr(), self.chunk_len.data_ptr(), self.n_chunks, self.lr, self.betas[0],
+                self.betas[1], self.eps, self.weight_decay, self.step_count, 1 if zero_grad else 0,
+                cabi.stream_ptr(buf.device)), "fmlp_adam_step_f32")

@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import math
 
-import numpy as np
 import torch
 
 from . import _cabi as cabi

@@ -260,6 +260,16 @@ int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const float* y, co
                              const int32_t* seg_class_distill, float* loss, float* dz, void* ws,
                              size_t ws_bytes, fmlp_stream_t stream);
 
+/* ------------------------------------------------------------------ fused Adam
+ * One torch.optim.Adam step (amsgrad=False; the optimizer the reference re-creates every round,
+ * utils/local_training.py:912,1149) over the PARAMETER runs of flat fp32 buffers p/g/m/v that
+ * share one layout.  chunk_start_dev / chunk_len_dev (device arrays [n_chunks], len <= 2048)
+ * enumerate those runs; `step` is the 1-based step count; zero_grad != 0 also clears g.         */
+int fmlp_adam_step_f32(float* p, float* g, float* m, float* v, const int64_t* chunk_start_dev,
+                       const int32_t* chunk_len_dev, int64_t n_chunks, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int64_t step, int zero_grad,
+                       fmlp_stream_t stream);
+
 /* dz[i] *= *scale_dev  (upstream gradient of the scalar loss, read from device memory). */
 int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream);
 

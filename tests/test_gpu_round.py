@@ -14,7 +14,6 @@ DEV = "cuda"
 
 @pytest.mark.parametrize("mode", ["pair", "folded"])
 def test_round_hot_path_matches_per_client_oracle(lib, mode):
-    import fedmlp_b200 as F
     from fedmlp_b200.round import ClientShard
 
     C, D, P = 5, 256, 10007 + 1          # P multiple of 4

@@ -1,5 +1,5 @@
 """Micro-benchmark of the individual kernels with CUDA events (tuning aid, not the bench)."""
-import argparse, sys, os
+import argparse, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 ap = argparse.ArgumentParser()
@@ -18,7 +18,6 @@ if args.lib:
 import bench
 import fedmlp_b200 as F
 from fedmlp_b200.round import ClientShard
-a = bench.parse_args.__wrapped__() if hasattr(bench.parse_args, "__wrapped__") else None
 class A: pass
 a = A(); a.clients_per_gpu = args.clients; a.rows_per_client = args.rows; a.classes = args.classes; a.dim = args.dim; a.sim_mode = args.mode
 dev = torch.device("cuda", 0)

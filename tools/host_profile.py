@@ -26,7 +26,6 @@ t2 = time.perf_counter()
 print(f"host enqueue per step {(t1-t0)/20*1e3:.3f} ms; incl. drain {(t2-t0)/20*1e3:.3f} ms")
 # time individual C calls
 lib = cabi.lib()
-import ctypes
 names = ["fmlp_tag_sim_f32", "fmlp_tag_select", "fmlp_mask_fill", "fmlp_loss_stage2_f32", "fmlp_proto_build_f32", "fmlp_fedavg_flat_f32"]
 acc = {n: [0.0, 0] for n in names}
 class Wrap:
