@@ -50,6 +50,9 @@ SIGNATURES = {
     "fmlp_proto_ws_bytes": (_sz, [_i64, _i, _i, _i]),
     "fmlp_proto_build_f32": (_i, [_p, _i64, _i, _p, _p, _i, _i, _i, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _sz, _p]),
     "fmlp_tag_sim_f32": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p, _p, _i64, _i, _p]),
+    "fmlp_sim_table_bytes": (_sz, [_i, _i]),
+    "fmlp_sim_table_build_f32": (_i, [_p, _i, _i, _u32, _i, _p, _p]),
+    "fmlp_pool_tag_f32": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _u32, _i, _p, _i64, _p, _i64, _p]),
     "fmlp_tag_select_ws_bytes": (_sz, [_i, _i, _i64]),
     "fmlp_tag_select": (_i, [_p, _i64, _p, _i64, _i, _i, _p, _p, _d, _d, _p, _p, _p, _i64, _p, _sz, _p]),
     "fmlp_mask_fill": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

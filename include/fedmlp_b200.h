@@ -190,6 +190,30 @@ int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const float* pro
                      int S, const int64_t* seg_rows, const uint32_t* seg_missing, float* sim,
                      int64_t ld_sim, int mode, fmlp_stream_t stream);
 
+/* ------------------------------------------------------------------ K3 fused into feature extraction
+ * (SURVEY §8f.1).  The reference's tagging pass keeps, per batch, only the pooled feature of the
+ * backbone's last feature map, `features, _ = net(images1)` (utils/local_training.py:1033-1036;
+ * the model tail is flatten(adaptive_avg_pool2d(relu(fmap), 1))), concatenates them over the
+ * dataset (:1037, quadratic torch.cat) and scores the result (:1052-1058).  fmlp_pool_tag_f32 does
+ * pooling and scoring in one pass over the feature map of a batch:
+ *     feat[b, d] = (1/HW) * sum_hw act(fmap[b, d, hw])      act = relu if `relu` != 0, else identity
+ *     sim[c][b]  = cos(feat_b, P[2c]) - cos(feat_b, P[2c+1])   for every class c in `classes`
+ *   fmap     [B, D, HW] (FMLP_FMAP_NCHW) or [B, HW, D] (FMLP_FMAP_NHWC, channels_last), dense, 16-B
+ *            aligned, D % 4 == 0, HW <= 256
+ *   table    class vectors built once per round by fmlp_sim_table_build_f32 from the aggregated
+ *            prototypes [2C, D] with the SAME `classes` and `mode`; fmlp_sim_table_bytes(C, D) bytes
+ *   feat     [B, ld_feat] out (what the classifier consumes) or NULL
+ *   sim      [C, ld_sim] class-major, already offset to the batch's first column; column b is
+ *            written for the classes in `classes`; NULL iff classes == 0 (pooling only)
+ *   mode     FMLP_SIM_PAIR (<= 16 classes per launch) or FMLP_SIM_FOLDED                       */
+enum { FMLP_FMAP_NCHW = 0, FMLP_FMAP_NHWC = 1 };
+size_t fmlp_sim_table_bytes(int C, int D);
+int fmlp_sim_table_build_f32(const float* proto, int C, int D, uint32_t classes, int mode,
+                             float* table, fmlp_stream_t stream);
+int fmlp_pool_tag_f32(const float* fmap, int layout, int B, int D, int HW, int relu,
+                      const float* table, int C, uint32_t classes, int mode, float* feat,
+                      int64_t ld_feat, float* sim, int64_t ld_sim, fmlp_stream_t stream);
+
 /* ------------------------------------------------------------------ K3b: selection
  * Replaces utils/local_training.py:1061-1112 + utils/utils.py:24-35 (max_m_indices /
  * min_n_indices).  Per (segment, missing class), over the candidate rows (tag == 0):

@@ -158,6 +158,24 @@ def tag_similarity(features, prototype, missing_classes):
     return out
 
 
+def pooled_features(fmap, relu=True):
+    """Tail of the reference's model forward, the `features` of `features, _ = net(images1)`
+    (utils/local_training.py:1033-1036): torchvision densenet.py DenseNet.forward as patched by the
+    authors (not vendored): relu -> adaptive_avg_pool2d(1) -> flatten.  EfficientNet's
+    tail has no relu.  fmap [B, D, H, W] -> [B, D]."""
+    x = torch.clamp_min(fmap, 0) if relu else fmap
+    b, d = x.shape[0], x.shape[1]
+    x = x.reshape(b, d, -1)
+    return x.sum(dim=2) / x.shape[2]
+
+
+def pool_tag(fmap, prototype, missing_classes, relu=True):
+    """pooled features of one batch and their tagging similarities
+    (utils/local_training.py:1033-1036 followed by :1052-1058 on those rows)."""
+    feat = pooled_features(fmap, relu)
+    return feat, tag_similarity(feat, prototype, missing_classes)
+
+
 # ------------------------------------------------------------------------------------ a7
 def top_positions_python(values, n, largest):
     """utils/utils.py:24-35 max_m_indices / min_n_indices, literally: Python's stable sort of

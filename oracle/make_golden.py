@@ -32,6 +32,7 @@ from pathlib import Path
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from oracle import ref_loader
@@ -176,6 +177,36 @@ def make_tagging(ref):
         out[f"ties/max/{n}"] = np.array(ref.utils.max_m_indices(vals, n), dtype=np.int64)
         out[f"ties/min/{n}"] = np.array(ref.utils.min_n_indices(vals, n), dtype=np.int64)
     np.savez_compressed(GOLDEN_DIR / "tagging.npz", **out)
+
+
+def make_pool(ref):
+    """Fused pooling + tagging: the feature the reference tags is the tail of the model
+    forward, `features = self.features(x); out = F.relu(features); out = F.adaptive_avg_pool2d(out,
+    (1, 1)); out = torch.flatten(out, 1)` (torchvision densenet.py DenseNet.forward, which the authors
+    patched to return (out, logits); not vendored).  The tail is run here through the
+    installed torchvision DenseNet class itself (features = Identity, classifier = Identity) and the
+    similarities through the reference's CosineSimilarityFast."""
+    import torchvision
+    g = torch.Generator().manual_seed(77)
+    B, D, H, W, C = 9, 40, 7, 7, 5
+    net = torchvision.models.DenseNet(growth_rate=4, block_config=(1,), num_init_features=8, num_classes=C)
+    net.features = nn.Identity()
+    net.classifier = nn.Identity()
+    net.eval()
+    fmap = torch.randn(B, D, H, W, generator=g)
+    fmap[3, 7] = -1.0                                  # a channel that pools to exactly 0
+    with torch.no_grad():
+        feat = net(fmap.clone())                       # relu (in place) + avg-pool + flatten
+        feat_norelu = F.adaptive_avg_pool2d(fmap, (1, 1)).flatten(1)   # EfficientNet tail: no relu
+    proto = torch.relu(torch.randn(2 * C, D, generator=g)) + 0.1
+    out = {"fmap": _np(fmap), "feat": _np(feat), "feat_norelu": _np(feat_norelu), "proto": _np(proto)}
+    model = ref.local_training.CosineSimilarityFast()
+    for c in range(C):
+        for tag, f in (("", feat), ("_norelu", feat_norelu)):
+            c0 = model(f, torch.unsqueeze(proto[2 * c], dim=0))
+            c1 = model(f, torch.unsqueeze(proto[2 * c + 1], dim=0))
+            out[f"sim{tag}/{c}"] = _np(c0 - c1)
+    np.savez_compressed(GOLDEN_DIR / "pool.npz", **out)
 
 
 # ----------------------------------------------------------------------------------- synthetic dataset / model
@@ -437,6 +468,7 @@ def main():
     make_fedavg(ref)
     make_aggregators(ref)
     make_tagging(ref)
+    make_pool(ref)
     make_maskfill(ref)
     make_flow(ref)
     for p in sorted(GOLDEN_DIR.glob("*.npz")):

@@ -215,3 +215,16 @@ def test_other_aggregators_match_reference():
     with np.errstate(all="ignore"):
         out = O.fedavg_rela(protos, dict_len, gu.parse_lists(z["rela/lists"]))
     np.testing.assert_array_equal(out.numpy(), z["rela/out"])
+
+
+def test_pooled_features_and_sims_match_reference():
+    """the oracle's model-tail restatement against torchvision's DenseNet.forward tail and
+    the reference's CosineSimilarityFast (tests/golden/pool.npz, oracle/make_golden.py:make_pool)."""
+    z = gu.load("pool.npz")
+    fmap, proto = torch.from_numpy(z["fmap"]), torch.from_numpy(z["proto"])
+    for tag, relu in (("", True), ("_norelu", False)):
+        feat, sims = O.pool_tag(fmap, proto, list(range(5)), relu=relu)
+        np.testing.assert_allclose(feat.numpy(), z["feat" + tag], rtol=1e-6, atol=1e-8)
+        for c in range(5):
+            np.testing.assert_allclose(sims[c].numpy(), z[f"sim{tag}/{c}"], rtol=0, atol=1e-6)
+    assert O.pooled_features(fmap)[3, 7] == 0.0
