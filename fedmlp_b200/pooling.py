@@ -94,8 +94,39 @@ def pool_tag(fmap: torch.Tensor, table: SimTable | None = None, sim_out: torch.T
             raise ValueError("batch does not fit in sim_out")
         tab_ptr, C, classes, mode = table.data.data_ptr(), table.C, table.classes, table.mode
         sim_ptr, ld_sim = sim_out.data_ptr() + 4 * col0, sim_out.stride(0)
+    if B == 0:
+        return feat_out[:0] if feat_out is not None else None
     with torch.cuda.device(dev):
         cabi.check(cabi.lib().fmlp_pool_tag_f32(fmap.data_ptr(), layout, B, D, HW, int(bool(relu)), tab_ptr, C, classes, mode,
                                                 feat_ptr, ld_feat, sim_ptr, ld_sim, cabi.stream_ptr(dev)),
                    "fmlp_pool_tag_f32")
     return feat_out[:B] if feat_out is not None else None
+
+
+class FusedTail(torch.nn.Module):
+    """`net(x) -> (feature, logits)` (the model contract of the reference) for a backbone
+    split into `features` (-> [B, D, H, W]) and `classifier` (Linear on [B, D]).
+
+    Under torch.no_grad() — the reference's tagging and prototype passes
+    (utils/local_training.py:1033, 1223) — the tail runs in the fused kernel; `tagging(x, ...)`
+    additionally writes the batch's similarities.  With autograd enabled (training steps) the tail is
+    the stock torch relu / adaptive_avg_pool2d chain, which is backbone work outside this library."""
+
+    def __init__(self, features: torch.nn.Module, classifier: torch.nn.Module, relu: bool = True):
+        super().__init__()
+        self.features, self.classifier, self.relu = features, classifier, relu
+
+    def forward(self, x):
+        fmap = self.features(x)
+        if torch.is_grad_enabled() and (fmap.requires_grad or self.training):
+            out = torch.relu(fmap) if self.relu else fmap
+            feat = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(out, (1, 1)), 1)
+        else:
+            feat = pool_tag(fmap, relu=self.relu)
+        return feat, self.classifier(feat)
+
+    @torch.no_grad()
+    def tagging(self, x, table: SimTable, sim_out: torch.Tensor, col0: int):
+        """One batch of the tagging pass: features, logits, and sim_out[:, col0:col0+B] filled."""
+        feat = pool_tag(self.features(x), table, sim_out=sim_out, col0=col0, relu=self.relu)
+        return feat, self.classifier(feat)

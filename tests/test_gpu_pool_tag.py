@@ -141,3 +141,29 @@ def test_streamed_tagging_equals_batched(P, lib):
                 for row in set(sa[0, c, side, :n].tolist()) ^ set(sel[key]):
                     cut = ref_vals[sel[key][-1]]
                     assert abs(ref_vals[row] - cut) < 2e-6
+
+
+def test_fused_tail_module(P):
+    """FusedTail keeps the reference's `net(x) -> (feature, logits)` contract: kernel tail under no_grad,
+    torch tail with autograd, identical values; tagging() fills the similarity columns."""
+    torch.manual_seed(3)
+    feats = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 3, stride=2, padding=1), torch.nn.BatchNorm2d(64)).to(DEV)
+    net = P.FusedTail(feats, torch.nn.Linear(64, 5).to(DEV)).eval()
+    x = torch.randn(10, 3, 14, 14, device=DEV)
+    with torch.no_grad():
+        f0, z0 = net(x)
+    net.train()
+    f1, z1 = net(x)          # autograd path (BatchNorm in train mode differs, so compare in eval below)
+    assert f1.requires_grad
+    net.eval()
+    f2, z2 = net(x)          # grad enabled, eval: torch tail
+    np.testing.assert_allclose(f0.cpu().numpy(), f2.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(z0.cpu().numpy(), z2.detach().cpu().numpy(), rtol=1e-4, atol=1e-6)
+    proto = torch.rand(10, 64, device=DEV) + 0.05
+    table = P.build_sim_table(proto, [0, 2, 3], "pair")
+    sim = torch.full((5, 16), float("nan"), device=DEV)
+    f3, _ = net.tagging(x, table, sim, 4)
+    ref = O.tag_similarity(f0.cpu(), proto.cpu(), [0, 2, 3])
+    for c in (0, 2, 3):
+        np.testing.assert_allclose(sim[c, 4:14].cpu().numpy(), ref[c].numpy(), rtol=0, atol=2e-6)
+    assert torch.isnan(sim[1]).all() and torch.isnan(sim[:, :4]).all()
