@@ -12,17 +12,20 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
-    print("kernel:", d.get("Kernel Name"), "grid", d.get("Grid Size"), "block", d.get("Block Size"))
-    for k in KEYS:
-        if k in d: print(f"  {k:70s} {d[k]:>18s} {u[k]}")
-    stalls = [(k, float(d[k].replace(',', ''))) for k in hdr if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio") and d[k]]
-    stalls = [(k, v) for k, v in stalls]
-    if not stalls:
-        stalls = [(k, float(d[k].replace(',', ''))) for k in hdr if "warp_issue_stalled" in k and k.endswith(".ratio") and d[k]]
-    for k, v in sorted(stalls, key=lambda x: -x[1])[:8]:
-        print(f"  stall {k:80s} {v:10.3f}")
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        if len(vals) != len(hdr):
+            continue
+        d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
+        print("kernel:", d.get("Kernel Name"), "grid", d.get("Grid Size"), "block", d.get("Block Size"))
+        for k in KEYS:
+            if k in d: print(f"  {k:70s} {d[k]:>18s} {u[k]}")
+        stalls = [(k, float(d[k].replace(',', ''))) for k in hdr if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio") and d[k]]
+        if not stalls:
+            stalls = [(k, float(d[k].replace(',', ''))) for k in hdr if "warp_issue_stalled" in k and k.endswith(".ratio") and d[k]]
+        for k, v in sorted(stalls, key=lambda x: -x[1])[:8]:
+            print(f"  stall {k:80s} {v:10.3f}")
+        print()
 if __name__ == "__main__":
     for p in sys.argv[1:]:
         main(p); print()
