@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--graph-multi", type=int, default=0,
+                    help="N>1 with the fused collective: 1 = replay the round (incl. the fold+all-reduce kernel) as a CUDA graph")
     ap.add_argument("--proto-on-side", type=int, default=1,
                     help="N>1: 1 = prototypes share the side stream with the aggregation, 0 = stay on the main chain")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
@@ -359,7 +361,7 @@ def gpu_arm(a):
     launches_per_step = None
     # N>1 stays eager: a graph serialises the cooperative fold+all-reduce kernel against the other
     # stream (measured slower) and NCCL capture is not used
-    if world == 1 and not a.no_graph:
+    if (world == 1 or (a.graph_multi and fused is not None)) and not a.no_graph:
         try:
             l0 = lib.fmlp_launch_count()
             g_ = torch.cuda.CUDAGraph()

@@ -42,7 +42,7 @@ SIGNATURES = {
     "fmlp_fedavg_flat_i64": (_i, [_p, _p, _i, _i64, _d, _i, _i, _p, _p]),
     "fmlp_fedavg_multi_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _i, _f, _i, _p]),
     "fmlp_fedavg_multi_i64": (_i, [_p, _p, _p, _p, _i64, _i, _p, _i, _d, _i, _i, _p]),
-    "fmlp_fedavg_allreduce_f32": (_i, [_p, _p, _i, _i64, _p, _p, _p, _i64, _i, _i, _p, _p]),
+    "fmlp_fedavg_allreduce_f32": (_i, [_p, _p, _i, _i64, _p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "fmlp_proto_avg_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fmlp_tao_avg_f64": (_i, [_p, _i, _i, _p, _p, _d, _p, _p]),
     "fmlp_model_dist_ws_bytes": (_sz, [_i64, _i]),

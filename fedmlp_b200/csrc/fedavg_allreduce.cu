@@ -7,44 +7,56 @@
 // local fold and then ncclAllReduce serialises 40 us of HBM streaming with ~70-110 us of all-reduce;
 // here the transfer overlaps the math slice by slice:
 //
-//   phase 1  for every slice s (staggered start so the G ranks hit G different links): fold this
-//            rank's K clients over the slice (HBM-bound, 8 x 128-bit loads in flight per thread,
-//            same arithmetic as fedavg_flat_kernel) and store the partial directly into rank s's
-//            inbox row [rank] with peer st.global -> the reduce-scatter traffic ((G-1)/G*4P bytes
-//            out) rides under the (K+... )*4P bytes of local reads.
-//   barrier  __threadfence_system + grid.sync, then one release-store per peer of this call's
-//            epoch into the peer's flag word; every CTA acquires the G flags of its own rank.
-//   phase 2  sum the G inbox rows of the own slice in FIXED rank order (deterministic, and every
-//            element of the result is computed by exactly one rank, so all ranks hold bit-identical
-//            parameters) and store the result slice into every rank's result buffer (all-gather by
-//            peer stores), then the same barrier so the result is complete when the kernel ends.
+//   fold     for every chunk c of the parameter vector and every slice s of it (staggered start so
+//            the G ranks hit G different links): fold this rank's K clients over the slice (HBM-bound,
+//            8 x 128-bit loads in flight per thread, same arithmetic as fedavg_flat_kernel) and store
+//            the partial directly into rank s's inbox row [rank] with peer st.global -> the
+//            reduce-scatter traffic ((G-1)/G*4P bytes out) rides under the K*4P bytes of local reads.
+//            The CTA that finishes a chunk last (device counter) release-stores this call's epoch into
+//            every peer's flag word of that chunk.
+//   reduce   one chunk behind the fold: acquire the G flags of the chunk, sum the G inbox rows of the
+//            own slice in FIXED rank order (deterministic, and every element of the result is
+//            computed by exactly one rank, so all ranks hold bit-identical parameters), store the
+//            result slice into every rank's result buffer (all-gather by peer stores) and signal the
+//            chunk the same way.  The kernel ends when all peers' result chunks have landed.
+// No grid-wide barrier, no second kernel: the two transfer directions of neighbouring chunks overlap
+// each other and the fold (r01: 118 us with two global barriers at 8 GPUs).
 //
 // Buffers (stage inbox [G][L], result [G*L], flags [2][8]) are symmetric-memory allocations
 // made and exchanged by the host (torch.distributed._symmetric_memory); the kernel only sees raw
 // peer pointers.  Weights arrive pre-normalised (n_k / sum n), so no divide pass is needed.
-#include <cooperative_groups.h>
-
 #include <cstdlib>
 
 #include "common.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace fmlp {
 
 constexpr int kArMaxRanks = 8;
+constexpr int kArMaxChunks = FMLP_AR_MAX_CHUNKS;
 constexpr int kArThreads = 256;
 constexpr int kArUnroll = 8;
+
+// Flag words of one rank (uint32, symmetric memory, zero-initialised once):
+//   [phase 0..1][chunk][source rank]   epoch flags written by the peers (phase 0: "my partials of this
+//                                      chunk are in your inbox", phase 1: "my result slice of this chunk
+//                                      is in your result buffer")
+//   [phase 0..1][chunk]                local CTA counters (which CTA of this rank finishes a chunk last)
+//   [1]                                local CTA counter for the end of the call
+__host__ __device__ constexpr int ar_flag(int phase, int c, int g) { return (phase * kArMaxChunks + c) * kArMaxRanks + g; }
+__host__ __device__ constexpr int ar_count(int phase, int c) { return 2 * kArMaxChunks * kArMaxRanks + phase * kArMaxChunks + c; }
+constexpr int kArDoneCount = 2 * kArMaxChunks * kArMaxRanks + 2 * kArMaxChunks;
+static_assert(kArDoneCount < FMLP_AR_FLAG_WORDS, "flag buffer too small");
 
 struct ArArgs {
     const float* src[FMLP_MAX_CLIENTS];
     float w[FMLP_MAX_CLIENTS];
     float* stage[kArMaxRanks];      // stage[g] = rank g's inbox, [G][L]
     float* result[kArMaxRanks];     // result[g] = rank g's result buffer, >= G*L floats
-    uint32_t* flags[kArMaxRanks];   // flags[g] = rank g's flag words, [2][kArMaxRanks]
+    uint32_t* flags[kArMaxRanks];   // flags[g] = rank g's flag words
     int64_t P;                      // parameters (multiple of 4)
-    int64_t L;                      // slice length (multiple of 4), G*L >= P
-    int K, rank, G;
+    int64_t L;                      // floats per rank over all chunks = NC * Lc
+    int64_t Lc;                     // floats per (chunk, rank) slice (multiple of 4), G*L >= P
+    int K, rank, G, NC;
     uint32_t* epoch_dev;            // this rank's call counter (device memory, graph-replay safe)
 };
 
@@ -57,79 +69,116 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
-// All ranks have finished the phase: publish my epoch to every peer, wait for every peer's.
-__device__ __forceinline__ void rank_barrier(const ArArgs& a, uint32_t epoch, int phase, cg::grid_group& grid,
-                                             bool all_ctas_wait) {
-    __threadfence_system();   // this thread's peer stores are visible system-wide before the signal
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x < a.G)
-        st_release_sys(a.flags[threadIdx.x] + phase * kArMaxRanks + a.rank, epoch);
-    if (all_ctas_wait || blockIdx.x == 0) {
-        if (threadIdx.x < a.G) {
-            const uint32_t* f = a.flags[a.rank] + phase * kArMaxRanks + threadIdx.x;
-            // epochs only grow; "!=" would also do but ">=" tolerates a peer already in the next call
-            while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) { __nanosleep(64); }
-        }
-        __syncthreads();
+// This CTA has issued all its peer stores of (phase, chunk c).  The CTA of this rank that gets here
+// last publishes the rank's epoch to every peer.  Nobody waits here.
+__device__ __forceinline__ void signal_chunk(const ArArgs& a, uint32_t epoch, int phase, int c, int* s_last) {
+    __threadfence_system();   // this thread's peer stores are visible system-wide before the count
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t old = atomicAdd(a.flags[a.rank] + ar_count(phase, c), 1u);
+        *s_last = (old + 1u == epoch * gridDim.x);
+    }
+    __syncthreads();
+    if (*s_last && threadIdx.x < a.G) {
+        __threadfence_system();   // the other CTAs' stores, observed through the counter, come first
+        st_release_sys(a.flags[threadIdx.x] + ar_flag(phase, c, a.rank), epoch);
     }
 }
+// Every rank has published (phase, chunk c) of this call.
+__device__ __forceinline__ void wait_chunk(const ArArgs& a, uint32_t epoch, int phase, int c) {
+    if (threadIdx.x < a.G) {
+        const uint32_t* f = a.flags[a.rank] + ar_flag(phase, c, threadIdx.x);
+        // epochs only grow; ">=" tolerates a peer that is already in its next call
+        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) { __nanosleep(32); }
+    }
+    __syncthreads();
+}
 
+// The parameter vector is cut into NC chunks of G slices (slice s of every chunk belongs to rank s).
+// Per CTA:  fold(0), fold(1), reduce(0), fold(2), reduce(1), ...: the all-gather stores of chunk c-1 and
+// the reduce-scatter stores of chunk c+1 share the links while the fold keeps HBM busy; a chunk's
+// reduce only needs THAT chunk's partials from the peers, which were sent a whole chunk earlier.
+// There is no grid-wide barrier: the launch is cooperative only to guarantee that all CTAs are
+// resident (reduce(c) waits for the other CTAs' fold(c)).
 __global__ void __launch_bounds__(kArThreads, 4) fedavg_allreduce_kernel(const __grid_constant__ ArArgs a) {
-    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_last;
     // The epoch lives in device memory so that a CUDA-graph replay (identical kernel arguments)
-    // still advances it: every CTA reads it on entry, CTA 0 bumps it after the last barrier.
+    // still advances it: every CTA reads it on entry, the CTA that finishes last bumps it.
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_dev) + 1u;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const int64_t Lv = a.L >> 2;   // float4 per slice
-
-    // ---- phase 1: local fold, partial slices go straight to their owners ---------------------
-    for (int64_t idx = tid; idx < (int64_t)a.G * Lv; idx += nthreads) {
-        const int t = (int)(idx / Lv);
-        const int64_t v = idx - (int64_t)t * Lv;
-        int s = a.rank + 1 + t;
-        if (s >= a.G) s -= a.G;
-        const int64_t e = (int64_t)s * a.L + (v << 2);
-        if (e >= a.P) continue;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int i = 0;
-        for (; i + kArUnroll <= a.K; i += kArUnroll) {
-            float4 x[kArUnroll];
-#pragma unroll
-            for (int u = 0; u < kArUnroll; ++u) x[u] = ld_stream_f4(a.src[i + u] + e);
-#pragma unroll
-            for (int u = 0; u < kArUnroll; ++u) {
-                acc.x = fmaf(x[u].x, a.w[i + u], acc.x); acc.y = fmaf(x[u].y, a.w[i + u], acc.y);
-                acc.z = fmaf(x[u].z, a.w[i + u], acc.z); acc.w = fmaf(x[u].w, a.w[i + u], acc.w);
-            }
-        }
-        for (; i < a.K; ++i) {
-            const float4 x = ld_stream_f4(a.src[i] + e);
-            acc.x = fmaf(x.x, a.w[i], acc.x); acc.y = fmaf(x.y, a.w[i], acc.y);
-            acc.z = fmaf(x.z, a.w[i], acc.z); acc.w = fmaf(x.w, a.w[i], acc.w);
-        }
-        *reinterpret_cast<float4*>(a.stage[s] + (int64_t)a.rank * a.L + (v << 2)) = acc;   // peer store
-    }
-    rank_barrier(a, epoch, 0, grid, /*all_ctas_wait=*/true);
-
-    // ---- phase 2: reduce my slice in rank order, all-gather by peer stores ---------------------
+    const int64_t Lv = a.Lc >> 2;   // float4 per (chunk, rank) slice
     const float* inbox = a.stage[a.rank];
-    for (int64_t v = tid; v < Lv; v += nthreads) {
-        const int64_t e = (int64_t)a.rank * a.L + (v << 2);
-        if (e >= a.P) continue;
-        float4 acc = __ldcg(reinterpret_cast<const float4*>(inbox + (v << 2)));
-        for (int g = 1; g < a.G; ++g) {
-            const float4 x = __ldcg(reinterpret_cast<const float4*>(inbox + (int64_t)g * a.L + (v << 2)));
-            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+
+    for (int step = 0; step <= a.NC; ++step) {
+        if (step < a.NC) {
+            // ---- fold chunk `step`: partial slices go straight to their owners (staggered start so
+            //      the G ranks hit G different links)
+            const int64_t chunk0 = (int64_t)step * a.G * a.Lc;
+            for (int64_t idx = tid; idx < (int64_t)a.G * Lv; idx += nthreads) {
+                const int t = (int)(idx / Lv);
+                const int64_t v = idx - (int64_t)t * Lv;
+                int s = a.rank + 1 + t;
+                if (s >= a.G) s -= a.G;
+                const int64_t e = chunk0 + (int64_t)s * a.Lc + (v << 2);
+                if (e >= a.P) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int i = 0;
+                for (; i + kArUnroll <= a.K; i += kArUnroll) {
+                    float4 x[kArUnroll];
+#pragma unroll
+                    for (int u = 0; u < kArUnroll; ++u) x[u] = ld_stream_f4(a.src[i + u] + e);
+#pragma unroll
+                    for (int u = 0; u < kArUnroll; ++u) {
+                        acc.x = fmaf(x[u].x, a.w[i + u], acc.x); acc.y = fmaf(x[u].y, a.w[i + u], acc.y);
+                        acc.z = fmaf(x[u].z, a.w[i + u], acc.z); acc.w = fmaf(x[u].w, a.w[i + u], acc.w);
+                    }
+                }
+                for (; i < a.K; ++i) {
+                    const float4 x = ld_stream_f4(a.src[i] + e);
+                    acc.x = fmaf(x.x, a.w[i], acc.x); acc.y = fmaf(x.y, a.w[i], acc.y);
+                    acc.z = fmaf(x.z, a.w[i], acc.z); acc.w = fmaf(x.w, a.w[i], acc.w);
+                }
+                *reinterpret_cast<float4*>(a.stage[s] + (int64_t)a.rank * a.L + (int64_t)step * a.Lc + (v << 2)) = acc;   // peer store
+            }
+            signal_chunk(a, epoch, 0, step, &s_last);
         }
-        for (int g = 0; g < a.G; ++g) {
-            int dst = a.rank + g;           // start with the local copy, then walk the peers
-            if (dst >= a.G) dst -= a.G;
-            *reinterpret_cast<float4*>(a.result[dst] + e) = acc;
+        if (step >= 1) {
+            // ---- reduce my slice of chunk c in rank order (deterministic; every element of the result
+            //      is computed by exactly one rank, so all ranks hold bit-identical parameters) and
+            //      all-gather it by peer stores
+            const int c = step - 1;
+            wait_chunk(a, epoch, 0, c);
+            const int64_t e0 = (int64_t)c * a.G * a.Lc + (int64_t)a.rank * a.Lc;
+            const float* in_c = inbox + (int64_t)c * a.Lc;
+            for (int64_t v = tid; v < Lv; v += nthreads) {
+                const int64_t e = e0 + (v << 2);
+                if (e >= a.P) continue;
+                float4 acc = __ldcg(reinterpret_cast<const float4*>(in_c + (v << 2)));
+                for (int g = 1; g < a.G; ++g) {
+                    const float4 x = __ldcg(reinterpret_cast<const float4*>(in_c + (int64_t)g * a.L + (v << 2)));
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                }
+                for (int g = 0; g < a.G; ++g) {
+                    int dst = a.rank + g;           // start with the local copy, then walk the peers
+                    if (dst >= a.G) dst -= a.G;
+                    *reinterpret_cast<float4*>(a.result[dst] + e) = acc;
+                }
+            }
+            signal_chunk(a, epoch, 1, c, &s_last);
         }
     }
-    rank_barrier(a, epoch, 1, grid, /*all_ctas_wait=*/false);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.epoch_dev = epoch;   // after grid.sync: everyone has read it
+    // ---- the call is complete when every peer's result slices of every chunk have landed here
+    if (blockIdx.x == 0)
+        for (int c = 0; c < a.NC; ++c) wait_chunk(a, epoch, 1, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t old = atomicAdd(a.flags[a.rank] + kArDoneCount, 1u);
+        if (old + 1u == epoch * gridDim.x) {   // every CTA of this rank has read the epoch and is done
+            __threadfence();
+            *a.epoch_dev = epoch;
+        }
+    }
 }
 
 }  // namespace fmlp
@@ -138,12 +187,12 @@ using namespace fmlp;
 
 extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* weights, int K, int64_t P,
                                          float* const* stage_ptrs, float* const* result_ptrs,
-                                         uint32_t* const* flag_ptrs, int64_t slice_len, int rank, int world,
-                                         uint32_t* epoch_dev, fmlp_stream_t stream) {
+                                         uint32_t* const* flag_ptrs, int64_t slice_len, int n_chunks, int rank,
+                                         int world, uint32_t* epoch_dev, fmlp_stream_t stream) {
     if (!srcs || !weights || !stage_ptrs || !result_ptrs || !flag_ptrs || !epoch_dev || K < 1 || K > FMLP_MAX_CLIENTS || P < 0 ||
-        world < 1 || world > kArMaxRanks || rank < 0 || rank >= world)
+        world < 1 || world > kArMaxRanks || rank < 0 || rank >= world || n_chunks < 1 || n_chunks > kArMaxChunks)
         return FMLP_ERR_BAD_ARG;
-    if ((P & 3) || (slice_len & 3) || slice_len * world < P) return FMLP_ERR_UNSUPPORTED;
+    if ((P & 3) || slice_len % (4 * (int64_t)n_chunks) || slice_len * world < P) return FMLP_ERR_UNSUPPORTED;
     ArArgs a;
     for (int i = 0; i < FMLP_MAX_CLIENTS; ++i) {
         a.src[i] = i < K ? srcs[i] : nullptr;
@@ -157,7 +206,8 @@ extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* 
         if (g < world && (!stage_ptrs[g] || !result_ptrs[g] || !flag_ptrs[g] || !aligned16(stage_ptrs[g]) || !aligned16(result_ptrs[g])))
             return FMLP_ERR_BAD_ARG;
     }
-    a.P = P; a.L = slice_len; a.K = K; a.rank = rank; a.G = world; a.epoch_dev = epoch_dev;
+    a.P = P; a.L = slice_len; a.Lc = slice_len / n_chunks; a.NC = n_chunks;
+    a.K = K; a.rank = rank; a.G = world; a.epoch_dev = epoch_dev;
     const int sms = sm_count();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
     static int per_sm = 0;
@@ -170,9 +220,9 @@ extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* 
         // kernels during the NVLink-bound phases
         if (const char* e = getenv("FMLP_AR_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
     }
-    int64_t blocks = ((int64_t)world * (slice_len >> 2) + kArThreads - 1) / kArThreads;
-    if (blocks > (int64_t)sms * per_sm) blocks = (int64_t)sms * per_sm;
-    if (blocks < 1) blocks = 1;
+    // The per-chunk CTA counters compare against epoch * gridDim.x, so the grid depends on nothing but
+    // the device: one full wave (CTAs without work just count).
+    const int64_t blocks = (int64_t)sms * per_sm;
     void* args[] = {(void*)&a};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)fedavg_allreduce_kernel, dim3((unsigned)blocks), dim3(kArThreads),
                                                 args, 0, (cudaStream_t)stream);

@@ -79,7 +79,12 @@ class FusedFedAvgAllReduce:
     call is a single cooperative launch on the current stream.  Collective: all ranks call it with
     the same P.  Needs NVLink/P2P between the ranks' GPUs (torch symmetric memory)."""
 
-    def __init__(self, P: int, group=None, device=None):
+    FLAG_WORDS = 512      # FMLP_AR_FLAG_WORDS
+    MAX_CHUNKS = 16       # FMLP_AR_MAX_CHUNKS
+
+    def __init__(self, P: int, group=None, device=None, n_chunks=None):
+        import os
+
         import torch.distributed._symmetric_memory as symm
 
         self.group = group if group is not None else dist.group.WORLD
@@ -91,12 +96,16 @@ class FusedFedAvgAllReduce:
             raise ValueError("P must be a multiple of 4 (flat buffers are 16-byte padded)")
         self.P = int(P)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        L = (self.P + self.world - 1) // self.world
-        self.L = (L + 3) // 4 * 4
+        # pipeline chunks: the all-gather of chunk c-1 overlaps the fold + reduce-scatter of chunk c+1
+        if n_chunks is None:
+            n_chunks = int(os.environ.get("FMLP_AR_CHUNKS", "4"))
+        self.n_chunks = max(1, min(self.MAX_CHUNKS, int(n_chunks)))
+        per_slice = (self.P + self.world * self.n_chunks - 1) // (self.world * self.n_chunks)
+        self.L = (per_slice + 3) // 4 * 4 * self.n_chunks      # floats per rank over all chunks
         n = self.world * self.L
         self.stage = symm.empty(n, dtype=torch.float32, device=self.device)
         self.result = symm.empty(n, dtype=torch.float32, device=self.device)
-        self.flags = symm.empty(16, dtype=torch.int32, device=self.device)
+        self.flags = symm.empty(self.FLAG_WORDS, dtype=torch.int32, device=self.device)
         self.stage.zero_(); self.result.zero_(); self.flags.zero_()
         hs = symm.rendezvous(self.stage, self.group)
         hr = symm.rendezvous(self.result, self.group)
@@ -122,7 +131,7 @@ class FusedFedAvgAllReduce:
         with torch.cuda.device(self.device):
             cabi.check(cabi.lib().fmlp_fedavg_allreduce_f32(
                 cabi.ptr_array([b.data_ptr() for b in local_bufs]), cabi.f32_array(weights_normalised), K, self.P,
-                self.stage_ptrs, self.result_ptrs, self.flag_ptrs, self.L, self.rank, self.world,
+                self.stage_ptrs, self.result_ptrs, self.flag_ptrs, self.L, self.n_chunks, self.rank, self.world,
                 self.epoch_dev.data_ptr(),
                 cabi.stream_ptr(self.device)), "fmlp_fedavg_allreduce_f32")
         return self.result[:self.P]

@@ -110,15 +110,22 @@ int fmlp_fedavg_multi_i64(const int64_t* const* src_table_dev, float* const* dst
  *                    their weights PRE-NORMALISED by the global sum (n_k / sum over all ranks)
  *   stage_ptrs       host array [world]: every rank's inbox   (symmetric memory, world*slice_len floats)
  *   result_ptrs      host array [world]: every rank's result buffer (>= world*slice_len floats)
- *   flag_ptrs        host array [world]: every rank's flag words (16 x uint32, zero-initialised once)
- *   slice_len        floats per rank slice, multiple of 4, world*slice_len >= P;  P % 4 == 0
+ *   flag_ptrs        host array [world]: every rank's flag words (FMLP_AR_FLAG_WORDS x uint32,
+ *                    zero-initialised once, never touched by the host afterwards)
+ *   slice_len        floats per rank over all chunks, multiple of 4*n_chunks, world*slice_len >= P;
+ *                    P % 4 == 0
+ *   n_chunks         1..FMLP_AR_MAX_CHUNKS pipeline chunks: the all-gather of chunk c-1 overlaps the
+ *                    fold + reduce-scatter of chunk c+1
  *   epoch_dev        device uint32 of THIS rank, zero-initialised once; the kernel uses *epoch_dev+1
  *                    as the call's epoch and stores it back (so CUDA-graph replays stay in step)
- * Collective: every rank must launch it; the kernel returns when result_ptrs[rank] is complete. */
+ * Collective: every rank must launch it (same P, slice_len, n_chunks); the kernel returns when
+ * result_ptrs[rank] is complete. */
+#define FMLP_AR_MAX_CHUNKS 16
+#define FMLP_AR_FLAG_WORDS 512
 int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* weights, int K, int64_t P,
                               float* const* stage_ptrs, float* const* result_ptrs,
-                              uint32_t* const* flag_ptrs, int64_t slice_len, int rank, int world,
-                              uint32_t* epoch_dev, fmlp_stream_t stream);
+                              uint32_t* const* flag_ptrs, int64_t slice_len, int n_chunks, int rank,
+                              int world, uint32_t* epoch_dev, fmlp_stream_t stream);
 
 /* Prototype aggregation, replaces utils/FedAvg.py:72-93 `FedAvg_proto`:
  *   out[2c+j] = (sum over clients i in act(c), in list order, of protos[i][2c+j]*n_i) / sum n_i

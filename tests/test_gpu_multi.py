@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, K, P, ret):
+def _worker(rank, world, port, K, P, n_chunks, ret):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, K, P, ret):
         mine = list(range(rank * K, (rank + 1) * K))
         bufs = [all_bufs[i].cuda() for i in mine]
         wn = [weights[i] / total for i in mine]
-        fused = fd.FusedFedAvgAllReduce(P)
+        fused = fd.FusedFedAvgAllReduce(P, n_chunks=n_chunks)
         outs = []
         for it in range(3):                                   # epochs advance, buffers are reused
             out = fused(bufs, wn).clone()
@@ -46,11 +46,12 @@ def _worker(rank, world, port, K, P, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("K,P", [(3, 1000), (8, 1 << 20), (1, 4)])
-def test_fused_fedavg_allreduce_two_ranks(lib, K, P):
+@pytest.mark.parametrize("K,P,n_chunks", [(3, 1000, 4), (8, 1 << 20, 4), (1, 4, 4), (8, 1 << 20, 1), (5, 4 * 7771, 16),
+                                          (8, 7042752, 4)])
+def test_fused_fedavg_allreduce_two_ranks(lib, K, P, n_chunks):
     world = 2
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), K, P, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), K, P, n_chunks, ret), nprocs=world, join=True)
     g = torch.Generator().manual_seed(7)
     all_bufs = [torch.randn(P, generator=g) for _ in range(K * world)]
     weights = [5000 + 13 * i for i in range(K * world)]
