@@ -33,7 +33,11 @@ namespace fmlp {
 
 constexpr int kArMaxRanks = 8;
 constexpr int kArMaxChunks = FMLP_AR_MAX_CHUNKS;
-constexpr int kArThreads = 256;
+#ifndef FMLP_AR_THREADS
+#define FMLP_AR_THREADS 992
+#endif
+constexpr int kArThreads = FMLP_AR_THREADS;   // compute threads per CTA (+ one signal warp); one CTA per SM: every CTA's
+                                              // per-chunk release costs its SM ~1 us, so fewer, larger CTAs
 constexpr int kArUnroll = 8;
 
 // Flag words of one rank (uint32, symmetric memory, zero-initialised once):
@@ -69,44 +73,94 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
-// This CTA has issued all its peer stores of (phase, chunk c).  The CTA of this rank that gets here
-// last publishes the rank's epoch to every peer.  Nobody waits here.
-__device__ __forceinline__ void signal_chunk(const ArArgs& a, uint32_t epoch, int phase, int c, int* s_last) {
-    __threadfence_system();   // this thread's peer stores are visible system-wide before the count
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t old = atomicAdd(a.flags[a.rank] + ar_count(phase, c), 1u);
-        *s_last = (old + 1u == epoch * gridDim.x);
-    }
-    __syncthreads();
-    if (*s_last && threadIdx.x < a.G) {
-        __threadfence_system();   // the other CTAs' stores, observed through the counter, come first
-        st_release_sys(a.flags[threadIdx.x] + ar_flag(phase, c, a.rank), epoch);
-    }
+__device__ __forceinline__ void red_release_cta_shared(int* p, int v) {
+    asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-// Every rank has published (phase, chunk c) of this call.
+__device__ __forceinline__ int ld_acquire_cta_shared(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+
+constexpr int kArComputeWarps = kArThreads / 32;
+
+// Compute warps: "this warp has issued all its peer stores of (phase, chunk)".  No fence, no wait:
+// the signal warp makes them visible.  (An earlier version fenced in every compute thread at every
+// chunk boundary; the drain cost ~20 us per chunk at 2 GPUs.)
+__device__ __forceinline__ void warp_chunk_done(int* s_done) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) red_release_cta_shared(s_done, 1);
+}
+// Signal warp: once all compute warps of this CTA are done with (phase, chunk c), count the CTA with a
+// GPU-scope release; the CTA of this rank that gets here last acquires the count and publishes the
+// rank's epoch to every peer with a SYSTEM-scope release.  Only those G lanes of one CTA per (phase,
+// chunk) execute a system-scope fence: MEMBAR.SYS in every CTA cost ~20 us per chunk at 2 GPUs (r01:
+// 101 / 145 / 236 us for 1 / 4 / 8 chunks against 78 / 65 / 65 us with the fences compiled out).  The
+// chain peer stores -> release.cta (s_done) -> acquire.cta -> release.gpu (counter) -> acquire.gpu ->
+// release.sys (flag) -> acquire.sys is causality-ordered in the PTX memory model (every link is
+// morally strong at its own scope), so the stores are visible before the flag.
+__device__ __forceinline__ void signal_chunk(const ArArgs& a, uint32_t epoch, int phase, int c, const int* s_done) {
+    const int lane = threadIdx.x & 31;
+    int last = 0;
+    if (lane == 0) {
+        while (ld_acquire_cta_shared(s_done) < kArComputeWarps) { __nanosleep(20); }
+        uint32_t old;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.flags[a.rank] + ar_count(phase, c)) : "memory");
+        last = (old + 1u == epoch * gridDim.x);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    __syncwarp();   // lane 0's acquire is ordered before the other lanes' release stores
+    if (last && lane < a.G) st_release_sys(a.flags[lane] + ar_flag(phase, c, a.rank), epoch);
+}
+// Every rank has published (phase, chunk c) of this call (per warp: lanes poll one flag each).
 __device__ __forceinline__ void wait_chunk(const ArArgs& a, uint32_t epoch, int phase, int c) {
-    if (threadIdx.x < a.G) {
-        const uint32_t* f = a.flags[a.rank] + ar_flag(phase, c, threadIdx.x);
+    const int lane = threadIdx.x & 31;
+    if (lane < a.G) {
+        const uint32_t* f = a.flags[a.rank] + ar_flag(phase, c, lane);
         // epochs only grow; ">=" tolerates a peer that is already in its next call
         while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) { __nanosleep(32); }
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 // The parameter vector is cut into NC chunks of G slices (slice s of every chunk belongs to rank s).
-// Per CTA:  fold(0), fold(1), reduce(0), fold(2), reduce(1), ...: the all-gather stores of chunk c-1 and
-// the reduce-scatter stores of chunk c+1 share the links while the fold keeps HBM busy; a chunk's
-// reduce only needs THAT chunk's partials from the peers, which were sent a whole chunk earlier.
-// There is no grid-wide barrier: the launch is cooperative only to guarantee that all CTAs are
-// resident (reduce(c) waits for the other CTAs' fold(c)).
-__global__ void __launch_bounds__(kArThreads, 4) fedavg_allreduce_kernel(const __grid_constant__ ArArgs a) {
-    __shared__ int s_last;
+// Compute warps:  fold(0), fold(1), reduce(0), fold(2), reduce(1), ...: the all-gather stores of chunk
+// c-1 and the reduce-scatter stores of chunk c+1 share the links while the fold keeps HBM busy; a
+// chunk's reduce only needs THAT chunk's partials from the peers, which were sent a whole chunk
+// earlier.  The compute warps never fence and never meet at a barrier; a ninth warp per CTA does the
+// system-scope fences and the signalling behind them.  There is no grid-wide barrier: the launch is
+// cooperative only to guarantee that all CTAs are resident (reduce(c) waits for the other CTAs'
+// fold(c)).
+__global__ void __launch_bounds__(kArThreads + 32, (kArThreads + 32) > 512 ? 1 : (kArThreads + 32) > 320 ? 2 : 3) fedavg_allreduce_kernel(const __grid_constant__ ArArgs a) {
+    __shared__ int s_done[2][kArMaxChunks];
     // The epoch lives in device memory so that a CUDA-graph replay (identical kernel arguments)
-    // still advances it: every CTA reads it on entry, the CTA that finishes last bumps it.
+    // still advances it: every thread reads it on entry, the CTA that finishes last bumps it.
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_dev) + 1u;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (threadIdx.x < 2 * kArMaxChunks) (&s_done[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+
+    if (threadIdx.x >= kArThreads) {
+        // ------------------------------------------------------------------ signal warp
+        for (int step = 0; step <= a.NC; ++step) {
+            if (step < a.NC) signal_chunk(a, epoch, 0, step, &s_done[0][step]);
+            if (step >= 1) signal_chunk(a, epoch, 1, step - 1, &s_done[1][step - 1]);
+        }
+        // the call is complete when every peer's result slices of every chunk have landed here
+        if (blockIdx.x == 0)
+            for (int c = 0; c < a.NC; ++c) wait_chunk(a, epoch, 1, c);
+        if ((threadIdx.x & 31) == 0) {
+            const uint32_t old = atomicAdd(a.flags[a.rank] + kArDoneCount, 1u);
+            if (old + 1u == epoch * gridDim.x) {   // every CTA of this rank has read the epoch and is done
+                __threadfence();
+                *a.epoch_dev = epoch;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- compute warps
+    const int64_t tid = (int64_t)blockIdx.x * kArThreads + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kArThreads;
     const int64_t Lv = a.Lc >> 2;   // float4 per (chunk, rank) slice
     const float* inbox = a.stage[a.rank];
 
@@ -141,16 +195,16 @@ __global__ void __launch_bounds__(kArThreads, 4) fedavg_allreduce_kernel(const _
                 }
                 *reinterpret_cast<float4*>(a.stage[s] + (int64_t)a.rank * a.L + (int64_t)step * a.Lc + (v << 2)) = acc;   // peer store
             }
-            signal_chunk(a, epoch, 0, step, &s_last);
+            warp_chunk_done(&s_done[0][step]);
         }
         if (step >= 1) {
             // ---- reduce my slice of chunk c in rank order (deterministic; every element of the result
             //      is computed by exactly one rank, so all ranks hold bit-identical parameters) and
             //      all-gather it by peer stores
             const int c = step - 1;
-            wait_chunk(a, epoch, 0, c);
             const int64_t e0 = (int64_t)c * a.G * a.Lc + (int64_t)a.rank * a.Lc;
             const float* in_c = inbox + (int64_t)c * a.Lc;
+            if (tid - (threadIdx.x & 31) < Lv) wait_chunk(a, epoch, 0, c);   // warp-uniform: only warps with work poll
             for (int64_t v = tid; v < Lv; v += nthreads) {
                 const int64_t e = e0 + (v << 2);
                 if (e >= a.P) continue;
@@ -165,18 +219,7 @@ __global__ void __launch_bounds__(kArThreads, 4) fedavg_allreduce_kernel(const _
                     *reinterpret_cast<float4*>(a.result[dst] + e) = acc;
                 }
             }
-            signal_chunk(a, epoch, 1, c, &s_last);
-        }
-    }
-    // ---- the call is complete when every peer's result slices of every chunk have landed here
-    if (blockIdx.x == 0)
-        for (int c = 0; c < a.NC; ++c) wait_chunk(a, epoch, 1, c);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t old = atomicAdd(a.flags[a.rank] + kArDoneCount, 1u);
-        if (old + 1u == epoch * gridDim.x) {   // every CTA of this rank has read the epoch and is done
-            __threadfence();
-            *a.epoch_dev = epoch;
+            warp_chunk_done(&s_done[1][c]);
         }
     }
 }
@@ -213,7 +256,7 @@ extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* 
     static int per_sm = 0;
     if (per_sm == 0) {
         int b = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fedavg_allreduce_kernel, kArThreads, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fedavg_allreduce_kernel, kArThreads + 32, 0);
         if (e != cudaSuccess) return (int)e;
         per_sm = b < 1 ? 1 : (b > 4 ? 4 : b);
         // tuning knob: a smaller footprint leaves SM resources to the concurrent tagging/prototype
@@ -224,7 +267,7 @@ extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* 
     // the device: one full wave (CTAs without work just count).
     const int64_t blocks = (int64_t)sms * per_sm;
     void* args[] = {(void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)fedavg_allreduce_kernel, dim3((unsigned)blocks), dim3(kArThreads),
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)fedavg_allreduce_kernel, dim3((unsigned)blocks), dim3(kArThreads + 32),
                                                 args, 0, (cudaStream_t)stream);
     return e == cudaSuccess ? launch_status() : (int)e;
 }
