@@ -74,9 +74,9 @@ def fedavg_flat_distributed(local_bufs, local_weights, total_weight=None, out=No
 
 
 class FusedFedAvgAllReduce:
-    """Local K-way weighted fold + two-shot all-reduce over NVLink peer memory in ONE kernel per
-    rank (fedavg_allreduce.cu).  Symmetric-memory buffers are allocated and exchanged once; every
-    call is a single cooperative launch on the current stream.  Collective: all ranks call it with
+    """Local K-way weighted fold + chunk-pipelined two-shot all-reduce over NVLink peer memory in ONE
+    kernel per rank (fedavg_allreduce.cu).  Symmetric-memory buffers are allocated and exchanged once;
+    every call is a single cooperative launch on the current stream.  Collective: all ranks call it with
     the same P.  Needs NVLink/P2P between the ranks' GPUs (torch symmetric memory)."""
 
     FLAG_WORDS = 512      # FMLP_AR_FLAG_WORDS
@@ -98,7 +98,7 @@ class FusedFedAvgAllReduce:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         # pipeline chunks: the all-gather of chunk c-1 overlaps the fold + reduce-scatter of chunk c+1
         if n_chunks is None:
-            n_chunks = int(os.environ.get("FMLP_AR_CHUNKS", "4"))
+            n_chunks = int(os.environ.get("FMLP_AR_CHUNKS", "2"))   # r01 sweep: 2 is best at 2 and 8 GPUs
         self.n_chunks = max(1, min(self.MAX_CHUNKS, int(n_chunks)))
         per_slice = (self.P + self.world * self.n_chunks - 1) // (self.world * self.n_chunks)
         self.L = (per_slice + 3) // 4 * 4 * self.n_chunks      # floats per rank over all chunks
