@@ -56,6 +56,8 @@ SIGNATURES = {
     "fmlp_tag_select_ws_bytes": (_sz, [_i, _i, _i64]),
     "fmlp_tag_select": (_i, [_p, _i64, _p, _i64, _i, _i, _p, _p, _d, _d, _p, _p, _p, _i64, _p, _sz, _p]),
     "fmlp_mask_fill": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "fmlp_eval_ws_bytes": (_sz, [_i64, _i]),
+    "fmlp_eval_multilabel_f32": (_i, [_p, _p, _i64, _i, _i, _f, _p, _p, _p, _sz, _p]),
     "fmlp_loss_ws_bytes": (_sz, [_i64, _i]),
     "fmlp_loss_stage1_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _u32, _u32, _i, _p, _p, _p, _p, _sz, _p]),
     "fmlp_loss_stage2_f32": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _p]),

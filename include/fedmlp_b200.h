@@ -301,6 +301,20 @@ int fmlp_adam_step_f32(float* p, float* g, float* m, float* v, const int64_t* ch
                        float beta2, float eps, float weight_decay, int64_t step, int zero_grad,
                        fmlp_stream_t stream);
 
+/* ------------------------------------------------------------------ evaluation metrics
+ * Replaces the metric half of utils/evaluations.py:15-73 `globaltest` / :89-140 `classtest`: per class,
+ * sklearn average_precision_score and roc_curve + auc of the probabilities, and the integer sums behind
+ * utils/multilabel_metrixs.py (BACC, Recall, Precision, F1Measure, Hamming_Loss) on preds = probs > threshold.
+ *   scores  [N, C] fp32 logits (scores_are_probs == 0: p = sigmoid(z) in fp32) or probabilities
+ *   labels  [N, C] fp32 0/1
+ *   class_counts  device int32 [C][8] out: n_pos, n_neg, n_pred, tp, tn, mismatches, 0, 0
+ *   class_ap_auc  device double [C][2] out: AP_c, AUC_c (NaN for a class without positives / negatives)
+ * Exact (no sort: P_c x N pairwise counts), deterministic; ws: fmlp_eval_ws_bytes(N, C).          */
+size_t fmlp_eval_ws_bytes(int64_t N, int C);
+int fmlp_eval_multilabel_f32(const float* scores, const float* labels, int64_t N, int C,
+                             int scores_are_probs, float threshold, int32_t* class_counts,
+                             double* class_ap_auc, void* ws, size_t ws_bytes, fmlp_stream_t stream);
+
 /* dz[i] *= *scale_dev  (upstream gradient of the scalar loss, read from device memory). */
 int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream);
 

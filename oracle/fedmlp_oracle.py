@@ -325,6 +325,72 @@ def loss_and_grads(fn, *zs_and_rest, n_grad):
 
 
 # ------------------------------------------------------------------------------------ a5 + a7 flow
+# ------------------------------------------------------------------------------------ f4 evaluation
+def _binary_clf_curve(y_true, y_score):
+    """sklearn.metrics._ranking._binary_clf_curve (scikit-learn 1.x, the dependency behind
+    utils/evaluations.py:9-10; not vendored): stable sort by decreasing score, one point per distinct
+    score, cumulative true / false positives."""
+    y_true = (np.asarray(y_true) == 1)
+    y_score = np.asarray(y_score)
+    order = np.argsort(y_score, kind="mergesort")[::-1]
+    y_score, y_true = y_score[order], y_true[order]
+    distinct = np.where(np.diff(y_score))[0]
+    idx = np.r_[distinct, y_true.size - 1]
+    tps = np.cumsum(y_true, dtype=np.float64)[idx]
+    fps = 1 + idx - tps
+    return fps, tps
+
+
+def average_precision(y_true, y_score):
+    """sklearn average_precision_score (binary): -sum(diff(recall) * precision[:-1]) over the
+    precision-recall curve (thresholds reversed, final point (recall 0, precision 1) appended)."""
+    fps, tps = _binary_clf_curve(y_true, y_score)
+    ps = tps + fps
+    precision = np.zeros_like(tps)
+    np.divide(tps, ps, out=precision, where=(ps != 0))
+    recall = tps / tps[-1]
+    precision = np.hstack((precision[::-1], 1.0))
+    recall = np.hstack((recall[::-1], 0.0))
+    return float(-np.sum(np.diff(recall) * precision[:-1]))
+
+
+def roc_auc(y_true, y_score):
+    """sklearn roc_curve + auc (utils/evaluations.py:60-63): trapezoid over (fpr, tpr) with the origin."""
+    fps, tps = _binary_clf_curve(y_true, y_score)
+    fps, tps = np.r_[0.0, fps], np.r_[0.0, tps]
+    fpr, tpr = fps / fps[-1], tps / tps[-1]
+    return float(np.sum(np.diff(fpr) * (tpr[1:] + tpr[:-1]) / 2.0))
+
+
+def eval_metrics(all_probs, all_labels, threshold=0.5):
+    """utils/evaluations.py:35-73 (everything after the inference loop) with utils/multilabel_metrixs.py
+    restated on arrays.  all_probs float32 [N, C], all_labels 0/1 [N, C]."""
+    all_probs = np.asarray(all_probs)
+    y_true = np.asarray(all_labels)
+    y_pred = all_probs > threshold
+    n, c = y_true.shape
+    aps = [average_precision(y_true[:, i], all_probs[:, i]) for i in range(c)]
+    m_ap = torch.tensor(aps).mean()
+    bacc = r = f1 = p = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(c):
+            yt, yp = y_true.T[i], y_pred.T[i]
+            tp = np.sum(np.logical_and(yt, yp))
+            recall1 = tp / np.sum(yt)
+            recall0 = np.sum(~np.logical_or(yt, yp)) / (yt.size - np.count_nonzero(yt))
+            bacc += (recall0 + recall1) / 2
+            r += tp / np.sum(yt)
+            f1 += (2 * tp) / (np.sum(yt) + np.sum(yp))
+            if np.sum(yp) != 0:
+                p += tp / np.sum(yp)
+    hamming = 0
+    for i in range(n):
+        hamming += np.size(y_true[i] == y_pred[i]) - np.count_nonzero(y_true[i] == y_pred[i])
+    auroc = sum(roc_auc(y_true.T[i], all_probs.T[i]) for i in range(c)) / c
+    return {"mAP": m_ap, "BACC": bacc / c, "R": r / c, "F1": f1 / c, "auc": auroc, "P": p / c,
+            "hamming_loss": hamming / (n * c), "APs": aps}
+
+
 class TaggingState:
     """Cross-round tagging state of one client (self.traindata_idx / self.idxss,
     utils/local_training.py:1025,1088-1089,1111-1112,1197-1204)."""

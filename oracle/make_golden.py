@@ -209,6 +209,65 @@ def make_pool(ref):
     np.savez_compressed(GOLDEN_DIR / "pool.npz", **out)
 
 
+def make_eval(ref):
+    """Evaluation metrics: the reference's own `globaltest` / `classtest`
+    (utils/evaluations.py:15-73, :89-140; sklearn + utils/multilabel_metrixs.py) on a synthetic test set
+    with a tiny CPU model.  Shim: DataLoader workers -> 0 (same batches, same order)."""
+    import importlib
+    ev = importlib.import_module("utils.evaluations")
+    real_loader = ev.DataLoader
+    ev.DataLoader = lambda *a, **k: real_loader(*a, **{**k, "num_workers": 0})
+
+    class EvalSet(torch.utils.data.Dataset):
+        def __init__(self, n, c, dim, seed):
+            g = torch.Generator().manual_seed(seed)
+            self.targets = (torch.rand(n, c, generator=g) < torch.linspace(0.05, 0.4, c)).float().numpy()
+            self.targets[:3] = 0; self.targets[3:6] = 1          # every class has both labels
+            shift = torch.randn(c, dim, generator=g)
+            self.x = (0.7 * torch.randn(n, dim, generator=g) + torch.from_numpy(self.targets) @ shift).float()
+            self.x[50:60] = self.x[40:50]                          # duplicated inputs -> tied probabilities
+            self.x[200:203] = self.x[7]
+
+        def __getitem__(self, i):
+            return {"image": self.x[i], "target": self.targets[i]}
+
+        def __len__(self):
+            return len(self.targets)
+
+    class Net(nn.Module):
+        def __init__(self, dim, c):
+            super().__init__()
+            self.fc = nn.Linear(dim, c)
+
+        def forward(self, x):
+            return x, self.fc(x)
+
+    torch.manual_seed(11)
+    n, c, dim = 611, 5, 12
+    ds, net = EvalSet(n, c, dim, 5), Net(dim, c)
+    args = types.SimpleNamespace(batch_size=16, device="cpu", n_classes=c)
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = ev.globaltest(net, ds, args)
+        cls = [ev.classtest(net, ds, args, i) for i in range(c)]
+    with torch.no_grad():
+        logits = net(ds.x)[1]
+    out = {"logits": _np(logits), "probs": _np(torch.sigmoid(logits)), "labels": ds.targets.astype(np.float32)}
+    for k, v in res.items():
+        out[f"globaltest/{k}"] = np.array(float(v), dtype=np.float64)
+    for i, d in enumerate(cls):
+        for k, v in d.items():
+            out[f"classtest/{i}/{k}"] = np.array(float(v), dtype=np.float64)
+    # per-class sklearn values on a hand-made score vector with heavy ties
+    from sklearn.metrics import average_precision_score, roc_curve, auc
+    ys = np.array([1, 0, 1, 1, 0, 0, 1, 0, 0, 1, 0, 1], dtype=np.float32)
+    sc = np.array([0.9, 0.9, 0.5, 0.5, 0.5, 0.1, 0.1, 0.7, 0.7, 0.7, 0.3, 0.3], dtype=np.float32)
+    fpr, tpr, _ = roc_curve(ys, sc, pos_label=1)
+    out["ties/y"], out["ties/p"] = ys, sc
+    out["ties/ap"] = np.array(average_precision_score(ys, sc)); out["ties/auc"] = np.array(auc(fpr, tpr))
+    ev.DataLoader = real_loader
+    np.savez_compressed(GOLDEN_DIR / "eval.npz", **out)
+
+
 # ----------------------------------------------------------------------------------- synthetic dataset / model
 class SynthDataset(torch.utils.data.Dataset):
     """Same sample contract as dataset/all_dataset.py:23-41 (two-view dict, numpy target row)."""
@@ -469,6 +528,7 @@ def main():
     make_aggregators(ref)
     make_tagging(ref)
     make_pool(ref)
+    make_eval(ref)
     make_maskfill(ref)
     make_flow(ref)
     for p in sorted(GOLDEN_DIR.glob("*.npz")):

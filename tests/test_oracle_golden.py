@@ -228,3 +228,14 @@ def test_pooled_features_and_sims_match_reference():
         for c in range(5):
             np.testing.assert_allclose(sims[c].numpy(), z[f"sim{tag}/{c}"], rtol=0, atol=1e-6)
     assert O.pooled_features(fmap)[3, 7] == 0.0
+
+
+def test_eval_metrics_match_reference_globaltest():
+    """the oracle's restatement of sklearn AP / ROC-AUC and utils/multilabel_metrixs.py against
+    the reference's own globaltest() output (tests/golden/eval.npz, oracle/make_golden.py:make_eval)."""
+    z = gu.load("eval.npz")
+    r = O.eval_metrics(z["probs"], z["labels"])
+    for k in ("mAP", "BACC", "R", "F1", "auc", "P", "hamming_loss"):
+        assert abs(float(r[k]) - float(z[f"globaltest/{k}"])) <= 1e-12, k
+    assert abs(O.average_precision(z["ties/y"], z["ties/p"]) - float(z["ties/ap"])) <= 1e-15
+    assert abs(O.roc_auc(z["ties/y"], z["ties/p"]) - float(z["ties/auc"])) <= 1e-15
