@@ -148,6 +148,45 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
 
+    // ---- producer: one tile of R rows per warp, features through the cp.async ring.  The ring is
+    //      primed BEFORE the prototype prologue so the first DEPTH-1 batches are in flight while the
+    //      norms and the class vectors are staged (the ring is private to the warp and independent of them)
+    const int nchunks = Dpad >> 7;
+    constexpr int DEPTH = Cfg::DEPTH;
+    const int64_t n_tiles = (a.n_total + R - 1) / R;
+    const int64_t tile_stride = (int64_t)gridDim.x * nwarps;
+    const int64_t t_first = (int64_t)blockIdx.x * nwarps + warp;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sRing + (size_t)warp * Cfg::RING) + lane * 16;
+    // producer cursor: batch = (tile, chunk), runs DEPTH-1 batches ahead of the math.  All address
+    // arithmetic is running pointers / offsets (r01 ncu: a third of the instructions of the first
+    // ring version were IMAD/ISETP/SEL/LEA in this path); only the single ragged tile clamps rows.
+    int64_t t_issue = t_first;
+    int c_issue = 0;
+    uint32_t slot_issue = 0;                                        // byte offset of the ring slot
+    const float* g_tile = a.feat + t_first * R * a.ld_feat + lane * 4;  // row0 of the producer's tile
+    const int64_t g_stride = tile_stride * R * a.ld_feat;
+    const int64_t t_ragged = (a.n_total % R) ? n_tiles - 1 : -1;
+    auto issue = [&]() {
+        if (t_issue < n_tiles) {
+            const int col = c_issue * 128 + lane * 4;
+            const int bytes = (ALIGNED || col < D) ? 16 : 0;
+            const float* g = g_tile + (bytes ? c_issue * 128 : 0);
+            if (t_issue != t_ragged) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + r * a.ld_feat, bytes);
+            } else {
+                const int rmax = (int)(a.n_total - 1 - t_issue * R);  // rows past the end re-read the last row
+#pragma unroll
+                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + (r < rmax ? r : rmax) * a.ld_feat, bytes);
+            }
+            if (++c_issue == nchunks) { c_issue = 0; t_issue += tile_stride; g_tile += g_stride; }
+        }
+        cp_async_commit();  // empty groups keep the wait_group arithmetic uniform
+        slot_issue = (slot_issue + R * 512 == DEPTH * R * 512) ? 0u : slot_issue + R * 512;
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) issue();
+
     // ---- prologue: prototype norms, then stage the vectors ----------------------------
     // |P_j| = sqrt(sum p^2) (torch.norm), one warp per prototype row.
     for (int j = warp; j < 2 * NPAIR; j += nwarps) {
@@ -183,43 +222,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     for (int i = 0; i < H::h4; ++i) out_idx[i] = H::index_of(i, lane);
     float* scratch = sScratch + warp * Cfg::SCRATCH;
     const uint32_t sP_addr = (uint32_t)__cvta_generic_to_shared(sP) + lane * 16;
-    const int nchunks = Dpad >> 7;
 
-    // ---- main loop: one tile of R rows per warp, features through the cp.async ring --------
-    constexpr int DEPTH = Cfg::DEPTH;
-    const int64_t n_tiles = (a.n_total + R - 1) / R;
-    const int64_t tile_stride = (int64_t)gridDim.x * nwarps;
-    const int64_t t_first = (int64_t)blockIdx.x * nwarps + warp;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sRing + (size_t)warp * Cfg::RING) + lane * 16;
-    // producer cursor: batch = (tile, chunk), runs DEPTH-1 batches ahead of the math.  All address
-    // arithmetic is running pointers / offsets (r01 ncu: a third of the instructions of the first
-    // ring version were IMAD/ISETP/SEL/LEA in this path); only the single ragged tile clamps rows.
-    int64_t t_issue = t_first;
-    int c_issue = 0;
-    uint32_t slot_issue = 0;                                        // byte offset of the ring slot
-    const float* g_tile = a.feat + t_first * R * a.ld_feat + lane * 4;  // row0 of the producer's tile
-    const int64_t g_stride = tile_stride * R * a.ld_feat;
-    const int64_t t_ragged = (a.n_total % R) ? n_tiles - 1 : -1;
-    auto issue = [&]() {
-        if (t_issue < n_tiles) {
-            const int col = c_issue * 128 + lane * 4;
-            const int bytes = (ALIGNED || col < D) ? 16 : 0;
-            const float* g = g_tile + (bytes ? c_issue * 128 : 0);
-            if (t_issue != t_ragged) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + r * a.ld_feat, bytes);
-            } else {
-                const int rmax = (int)(a.n_total - 1 - t_issue * R);  // rows past the end re-read the last row
-#pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + (r < rmax ? r : rmax) * a.ld_feat, bytes);
-            }
-            if (++c_issue == nchunks) { c_issue = 0; t_issue += tile_stride; g_tile += g_stride; }
-        }
-        cp_async_commit();  // empty groups keep the wait_group arithmetic uniform
-        slot_issue = (slot_issue + R * 512 == DEPTH * R * 512) ? 0u : slot_issue + R * 512;
-    };
-#pragma unroll
-    for (int d = 0; d < DEPTH - 1; ++d) issue();
     uint32_t slot = 0;  // byte offset of the consumer's ring slot
 
     for (int64_t t = t_first; t < n_tiles; t += tile_stride) {
