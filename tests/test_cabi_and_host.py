@@ -52,9 +52,28 @@ def test_no_cpu_fallback():
         F.build_prototypes(x, torch.zeros(8, 5), None, [0], [1])
     with pytest.raises(FedMLPNativeError):
         F.fedmlp_stage2_loss(torch.zeros(4, 5), None, torch.zeros(4, 5), torch.zeros(4, 5))
+    with pytest.raises(FedMLPNativeError):
+        F.pool_tag(torch.zeros(2, 8, 7, 7))                       # fused model tail: CUDA tensors only
+    with pytest.raises(FedMLPNativeError):
+        from fedmlp_b200 import evaluation
+        evaluation.multilabel_metrics(torch.zeros(6, 3), torch.zeros(6, 3))
     if not torch.cuda.is_available():
         with pytest.raises(FedMLPNativeError):
             F.FedAvg([OrderedDict(w=torch.zeros(3))], [1])
+        with pytest.raises(Exception):
+            F.build_sim_table(torch.zeros(10, 8), [0])
+
+
+def test_new_entry_points_validate_arguments(lib):
+    """pool_tag / sim_table / eval / adam reject bad arguments before touching the device."""
+    import ctypes as C
+    null = C.c_void_p(0)
+    assert lib.fmlp_sim_table_bytes(5, 1024) >= (2 * 5 * 1024 + 10) * 4
+    assert lib.fmlp_sim_table_bytes(0, 1024) == 0
+    assert lib.fmlp_eval_ws_bytes(100, 5) > 0 and lib.fmlp_eval_ws_bytes(100, 0) == 0
+    assert lib.fmlp_pool_tag_f32(null, 0, 1, 8, 49, 1, null, 0, 0, 1, null, 0, null, 0, null) == -1
+    assert lib.fmlp_sim_table_build_f32(null, 5, 8, 1, 1, null, null) == -1
+    assert lib.fmlp_eval_multilabel_f32(null, null, 10, 3, 0, 0.5, null, null, null, 0, null) == -1
 
 
 def test_flat_layout_and_densenet_shapes():
