@@ -320,7 +320,8 @@ def gpu_arm(a):
             try:
                 from fedmlp_b200.dist import FusedFedAvgAllReduce
                 fused = FusedFedAvgAllReduce(inp["Ppad"], device=dev)
-                collective = "fused fold + two-shot all-reduce over NVLink peer memory (one kernel per rank)"
+                collective = (f"fused fold + chunk-pipelined two-shot all-reduce over NVLink peer memory "
+                              f"(one kernel per rank, {fused.n_chunks} chunks)")
             except Exception as exc:
                 fused = None
                 collective += f" (fused path unavailable: {type(exc).__name__}: {exc})"[:200]

@@ -99,9 +99,7 @@ class FusedFedAvgAllReduce:
         # pipeline chunks: the all-gather of chunk c-1 overlaps the fold + reduce-scatter of chunk c+1
         if n_chunks is None:
             n_chunks = int(os.environ.get("FMLP_AR_CHUNKS", "2"))   # r01 sweep: 2 is best at 2 and 8 GPUs
-        self.n_chunks = max(1, min(self.MAX_CHUNKS, int(n_chunks)))
-        per_slice = (self.P + self.world * self.n_chunks - 1) // (self.world * self.n_chunks)
-        self.L = (per_slice + 3) // 4 * 4 * self.n_chunks      # floats per rank over all chunks
+        self.n_chunks, self.L = self.chunk_layout(self.P, self.world, n_chunks)
         n = self.world * self.L
         self.stage = symm.empty(n, dtype=torch.float32, device=self.device)
         self.result = symm.empty(n, dtype=torch.float32, device=self.device)
@@ -117,6 +115,14 @@ class FusedFedAvgAllReduce:
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.device)   # per-rank call counter
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)          # every rank's flags are zero before anyone signals
+
+    @classmethod
+    def chunk_layout(cls, P: int, world: int, n_chunks: int):
+        """(n_chunks, L): the parameter vector is cut into n_chunks chunks of `world` slices of L / n_chunks
+        floats (a multiple of 4, so every slice is 16-byte aligned); L = floats per rank over all chunks."""
+        n_chunks = max(1, min(cls.MAX_CHUNKS, int(n_chunks)))
+        per_slice = (P + world * n_chunks - 1) // (world * n_chunks)
+        return n_chunks, (per_slice + 3) // 4 * 4 * n_chunks
 
     def __call__(self, local_bufs, weights_normalised):
         """Returns the [P] global weighted mean (a view of this rank's symmetric result buffer,

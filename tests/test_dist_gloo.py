@@ -114,3 +114,16 @@ def test_shard_clients_partitions():
             parts = [list(shard_clients(n, world, r)) for r in range(world)]
             assert sum(parts, []) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_fused_allreduce_chunk_layout():
+    """Host-side slicing of the fused fold + all-reduce kernel (fmlp_fedavg_allreduce_f32 contract:
+    slice_len % (4 * n_chunks) == 0 and world * slice_len >= P)."""
+    from fedmlp_b200.dist import FusedFedAvgAllReduce as A
+    for P in (4, 1000, 7042752, 100_000_000):
+        for world in (1, 2, 3, 4, 8):
+            for nc in (0, 1, 2, 4, 7, 16, 99):
+                n, L = A.chunk_layout(P, world, nc)
+                assert 1 <= n <= A.MAX_CHUNKS
+                assert L % (4 * n) == 0 and world * L >= P
+                assert world * (L - 4 * n) < P or L == 4 * n          # no more than one vector of padding per slice
