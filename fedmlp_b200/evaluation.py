@@ -41,13 +41,13 @@ def class_statistics(scores: torch.Tensor, labels: torch.Tensor, scores_are_prob
     return counts, ap_auc
 
 
-def multilabel_metrics(scores, labels, scores_are_probs=False, classid=None):
-    """The result dict of `globaltest` (classid None: mAP, BACC, R, F1, auc, P, hamming_loss) or of
-    `classtest` (classid given: BACC, R, F1, P of that class) from device-resident logits."""
-    counts, ap_auc = class_statistics(scores, labels, scores_are_probs)
-    cnt = counts.cpu().numpy().astype(np.int64)
-    aa = ap_auc.cpu().numpy()
-    N, C = scores.shape
+def metrics_from_class_statistics(cnt, aa, N, classid=None):
+    """Last arithmetic of globaltest / classtest on the per-class sums (host, C numbers), written the way
+    utils/multilabel_metrixs.py and utils/evaluations.py:41-73 write it.  cnt int [C, >=6] = n_pos, n_neg,
+    n_pred, tp, tn, mismatches; aa float64 [C, 2] = AP_c, AUC_c."""
+    cnt = np.asarray(cnt).astype(np.int64)
+    aa = np.asarray(aa, dtype=np.float64)
+    C = cnt.shape[0]
     n_pos, n_neg, n_pred, tp, tn, mism = (cnt[:, k] for k in range(6))
     with np.errstate(divide="ignore", invalid="ignore"):
         if classid is not None:                       # classtest, utils/evaluations.py:120-140
@@ -72,6 +72,13 @@ def multilabel_metrics(scores, labels, scores_are_probs=False, classid=None):
         return {"mAP": torch.tensor([float(v) for v in aa[:, 0]]).mean(),       # torch.tensor(APs).mean(), fp32 like the reference
                 "BACC": bacc / C, "R": r / C, "F1": f1 / C, "auc": auroc, "P": p / C,
                 "hamming_loss": int(mism.sum()) / (N * C)}
+
+
+def multilabel_metrics(scores, labels, scores_are_probs=False, classid=None):
+    """The result dict of `globaltest` (classid None: mAP, BACC, R, F1, auc, P, hamming_loss) or of
+    `classtest` (classid given: BACC, R, F1, P of that class) from device-resident logits."""
+    counts, ap_auc = class_statistics(scores, labels, scores_are_probs)
+    return metrics_from_class_statistics(counts.cpu().numpy(), ap_auc.cpu().numpy(), scores.shape[0], classid)
 
 
 @torch.no_grad()

@@ -6,6 +6,7 @@ import re
 from collections import OrderedDict
 from pathlib import Path
 
+import numpy as np
 import pytest
 import torch
 
@@ -112,3 +113,46 @@ def test_fedavg_tao_matches_oracle_bitwise():
     lists = [[1, 2], [0, 3], [], [0, 1, 2, 3], [2]]
     np.testing.assert_array_equal(F.FedAvg_tao(t, w, lists), O.fedavg_tao(t, w, lists))
     np.testing.assert_array_equal(F.FedAvg_tao(t, w), O.fedavg_tao(t, w))
+
+
+def test_eval_host_arithmetic_matches_reference_globaltest():
+    """Host half of the on-device evaluation (fedmlp_b200.evaluation.metrics_from_class_statistics): given the
+    per-class sums the kernel produces (computed here with numpy), the result dicts equal the reference's own
+    globaltest / classtest outputs (tests/golden/eval.npz)."""
+    import golden_util as gu
+    from fedmlp_b200.evaluation import metrics_from_class_statistics
+    from oracle import fedmlp_oracle as O
+    z = gu.load("eval.npz")
+    probs, y = z["probs"], z["labels"] != 0
+    pred = probs > 0.5
+    N, C = probs.shape
+    cnt = np.stack([y.sum(0), (~y).sum(0), pred.sum(0), (y & pred).sum(0), (~y & ~pred).sum(0), (y != pred).sum(0)], axis=1)
+    aa = np.array([[O.average_precision(y[:, c], probs[:, c]), O.roc_auc(y[:, c], probs[:, c])] for c in range(C)])
+    res = metrics_from_class_statistics(cnt, aa, N)
+    for k in ("mAP", "BACC", "R", "F1", "auc", "P", "hamming_loss"):
+        assert abs(float(res[k]) - float(z[f"globaltest/{k}"])) <= 1e-12, k
+    assert res["mAP"].dtype == torch.float32
+    for i in range(C):
+        one = metrics_from_class_statistics(cnt, aa, N, classid=i)
+        for k in ("BACC", "R", "F1", "P"):
+            assert abs(float(one[k]) - float(z[f"classtest/{i}/{k}"])) <= 1e-12, (i, k)
+    # a class nobody predicts: Precision skips it but still divides by C; F1 stays finite
+    cnt2 = cnt.copy(); cnt2[0, 2] = 0; cnt2[0, 3] = 0
+    r2 = metrics_from_class_statistics(cnt2, aa, N)
+    assert np.isfinite(r2["P"]) and np.isfinite(r2["F1"])
+
+
+def test_pool_layout_detection():
+    """pooling._layout_of: NCHW vs channels_last vs strided inputs (pure host logic)."""
+    from fedmlp_b200 import pooling
+    x = torch.zeros(2, 8, 7, 7)
+    assert pooling._layout_of(x)[1:] == (pooling.FMAP_NCHW, 49)
+    xl = x.contiguous(memory_format=torch.channels_last)
+    t, layout, hw = pooling._layout_of(xl)
+    assert layout == pooling.FMAP_NHWC and hw == 49 and t.data_ptr() == xl.data_ptr()
+    xs = torch.zeros(2, 16, 7, 7)[:, ::2]                 # neither layout: densified to NCHW
+    t, layout, hw = pooling._layout_of(xs)
+    assert layout == pooling.FMAP_NCHW and t.is_contiguous()
+    assert pooling._layout_of(torch.zeros(3, 8, 49))[1:] == (pooling.FMAP_NCHW, 49)
+    with pytest.raises(ValueError):
+        pooling._layout_of(torch.zeros(3, 8))
