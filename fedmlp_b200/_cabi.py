@@ -11,7 +11,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CLASSES = 32
 MAX_SEGMENTS = 64
 MAX_CLIENTS = 64

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FMLP_ABI_VERSION 1
+#define FMLP_ABI_VERSION 2 /* 2: fmlp_fedavg_allreduce_f32 takes n_chunks; pool_tag, sim_table, eval, adam entry points */
 #define FMLP_MAX_CLASSES 32   /* class bit masks are uint32_t                        */
 #define FMLP_MAX_SEGMENTS 64  /* segments (clients) per launch                        */
 #define FMLP_MAX_CLIENTS 64   /* client buffers folded per fedavg launch              */
