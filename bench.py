@@ -458,7 +458,11 @@ def gpu_arm(a):
     # ---- end to end: pinned host inputs -> H2D -> round -> D2H of every result, per step
     e2e = None
     if not a.skip_e2e:
-        e2e = run_e2e(a, inp, shard, step, fed_out, world, dev)
+        try:
+            e2e = run_e2e(a, inp, shard, step, fed_out, world, dev)
+        except Exception as exc:      # report instead of losing the whole line (same exception on every rank)
+            e2e = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
 
     line = None
