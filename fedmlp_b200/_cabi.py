@@ -11,7 +11,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CLASSES = 32
 MAX_SEGMENTS = 64
 MAX_CLIENTS = 64
@@ -49,7 +49,8 @@ SIGNATURES = {
     "fmlp_model_dist_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _sz, _p]),
     "fmlp_proto_ws_bytes": (_sz, [_i64, _i, _i, _i]),
     "fmlp_proto_build_f32": (_i, [_p, _i64, _i, _p, _p, _i, _i, _i, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _sz, _p]),
-    "fmlp_tag_sim_f32": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p, _p, _i64, _i, _p]),
+    "fmlp_tag_sim_ws_bytes": (_sz, [_i, _i]),
+    "fmlp_tag_sim_f32": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p, _p, _i64, _i, _p, _sz, _p]),
     "fmlp_sim_table_bytes": (_sz, [_i, _i]),
     "fmlp_sim_table_build_f32": (_i, [_p, _i, _i, _u32, _i, _p, _p]),
     "fmlp_pool_tag_f32": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _u32, _i, _p, _i64, _p, _i64, _p]),

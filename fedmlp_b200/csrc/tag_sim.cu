@@ -3,25 +3,42 @@
 // Replaces utils/local_training.py:1052-1058 + CosineSimilarityFast.forward (:1417-1435):
 //     sim[c][n] = cos(f_n, P[2c]) - cos(f_n, P[2c+1]),  cos(f,p) = (f.p) * (1/(|f|*|p|))
 // The reference re-reads the feature matrix four times per missing class (2 GEMV + 2 norms);
-// here each row is read ONCE and |f|^2 plus all 2*M dot products are accumulated together.
+// here each row is read ONCE and |f|^2 plus all dot products are accumulated together.
 //
-// Mapping: the prototype vectors of the classes to score live in shared memory for the whole
-// (persistent) CTA; each warp owns a tile of R consecutive rows and walks D in 128-column
-// chunks (one coalesced 512-B request per row per chunk, ping-pong buffered one chunk ahead).
-// The first version of this kernel was ISSUE-bound (ncu r01: 981 warp-instructions per row,
-// only 38 % of them FMAs), so this one is built to minimise instructions:
-//   * packed fp32 FMAs (fma.rn.f32x2 -> SASS FFMA2): features and prototypes are loaded as
-//     64-bit pairs, every accumulator is an (even, odd) pair -> half the FMA instructions;
-//   * a prototype pair read from smem feeds R rows, the chunk loop is unrolled x2 so the
-//     ping-pong needs no register moves, D % 128 == 0 is a template flag (no column predicates);
-//   * the R*(NV+1) per-lane partials are combined with a transposed (recursive-halving) warp
-//     reduction: ~V shuffles instead of 5V, then ONE lane per (row, class) does the epilogue
-//     from a per-warp smem scratch instead of all 32 lanes doing all of them redundantly.
-//   * features travel global -> shared with cp.async (LDGSTS) into a private ring per warp, DEPTH
-//     batches ahead of the math: B200 HBM wants ~100 KB in flight per SM (tools/exp_readpattern.cu)
-//     and the register file cannot hold that next to R*(NV+1) accumulator pairs.  Every lane reads
-//     back exactly the 16 bytes it copied, so the ring needs no cross-lane synchronisation.
-// Work per byte is (2M+1)/4 FMA; FMLP_SIM_FOLDED halves that for large C.
+// Round-2 design (the round-1 kernel staged 16-byte cp.async pieces per lane, split every row over
+// the 32 lanes of a warp and paid a cross-lane reduction per tile; ncu showed it issue/latency-bound
+// at 128 registers and 12 warps per SM, 0.66 of the HBM roof at C=5 and 0.41 at C=14):
+//   * THREAD PER ROW.  A tile is ROWS = 32*RT consecutive rows; lane l of every compute warp owns
+//     rows l, l+32, ... of the tile and keeps their RT*(NV+1) accumulators (packed fp32 pairs,
+//     fma.rn.f32x2 -> SASS FFMA2) in registers.  The class vectors are therefore the SAME address for
+//     all lanes: one broadcast LDS.128 (a single shared-memory wavefront) feeds 2*RT FFMA2, where the
+//     round-1 mapping needed a full 512-byte read per 2*R FFMA2.  No cross-lane reduction at all.
+//   * TMA staging.  Features travel global -> shared as 2-D tiled bulk tensor copies
+//     (cp.async.bulk.tensor.2d, SASS UTMALDG): one box = ROWS rows x 32 columns (128 bytes per row) in
+//     the 128-byte swizzle, so lanes reading "their" row at the same column hit 8 distinct 16-byte
+//     bank groups per quarter-warp: conflict-free without padding.  Each compute warp owns a private
+//     ring of S boxes and its lane 0 re-arms the mbarrier and issues the next box the moment the warp
+//     has consumed one: no registers are spent on loads in flight, no warp ever waits for another
+//     warp's data, and S-1 boxes per warp (64..160 KB per SM) are always in flight.
+//   * The W compute warps of a CTA split the COLUMNS of a tile (column group g of 32 goes to warp
+//     g % W: together they pull 128*W contiguous bytes of every row), so the unit of load balance is a
+//     tile per CTA — 860 tiles over 148 SMs at the bench shape — not a tile per warp.  Per tile the
+//     warps' partial sums meet in shared memory (fixed warp order: deterministic) and the 32*W threads
+//     share the epilogue in the reference's op order (norm product, reciprocal, multiply, subtract).
+//   * The class vectors (pair mode: the prototypes; folded: q_c, with its IEEE divides) are built ONCE
+//     by a small table kernel into the caller's workspace, in the [column quad][vector] order the inner
+//     loop reads, and every CTA of the main kernel pulls them with one bulk copy.  The main kernel is
+//     a programmatic dependent launch: it initialises its barriers and starts streaming features while
+//     the table kernel is still running and only waits (griddepcontrol.wait) before the table copy.
+//     (First round-2 version: every CTA rebuilt the table in its prologue — 32..130 dependent L2 round
+//     trips per thread, 10..30 us in front of a 45..90 us kernel.)
+// Work per byte is (NV+1)/4 FMA with NV = 2M (pair mode) or M (FMLP_SIM_FOLDED: one dot against
+// q_c = P0/|P0| - P1/|P1|).  fp32 FFMA2 only: TF32/BF16 tensor cores would flip signs at 1e-3.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace fmlp {
@@ -29,43 +46,38 @@ namespace fmlp {
 using u64 = unsigned long long;
 
 struct SimArgs {
-    const float* feat;
     const float* proto;
+    const float* table;   // workspace: [NG*8 column quads][NV] float4 class vectors, then [2*NPAIR] prototype norms
     float* sim;
-    int64_t ld_feat;
     int64_t ld_sim;
     int64_t n_total;
     int D;
-    int Dpad;  // D rounded up to 128 (smem row stride, zero padded)
+    int NG;       // column groups of 32 (D rounded up)
+    int S;        // ring stages per warp
     int C;
     int8_t cls[FMLP_MAX_CLASSES];  // classes scored by this launch (ascending), NPAIR entries
     SegTable seg;                  // mask_a = missing-class mask per segment
 };
 
+#ifndef FMLP_SIM_W
+#define FMLP_SIM_W 8
+#endif
+#ifndef FMLP_SIM_RT_SMALL
+#define FMLP_SIM_RT_SMALL 2
+#endif
+#ifndef FMLP_SIM_RT_LARGE
+#define FMLP_SIM_RT_LARGE 2
+#endif
+
 template <int NPAIR, bool FOLD>
 struct SimCfg {
     static constexpr int NV = FOLD ? NPAIR : 2 * NPAIR;
-    // rows per warp tile / threads per CTA: accumulators cost 2*R*(NV+1) registers, and the kernel
-    // needs >= 12 warps per SM to hide FFMA2 / LDS latency (r01 ncu at C=14: 4 rows x 14 vectors
-    // = 192 registers -> 8 warps -> 38 % issue utilisation), so R shrinks as NV grows.
-#ifndef FMLP_SIM_R_MID
-#define FMLP_SIM_R_MID 3
-#endif
-#ifndef FMLP_SIM_THREADS_MID
-#define FMLP_SIM_THREADS_MID 384
-#endif
-    static constexpr int R = (NV <= 10) ? 4 : (NV <= 16 ? FMLP_SIM_R_MID : 2);
-#ifndef FMLP_SIM_THREADS_SMALL
-#define FMLP_SIM_THREADS_SMALL 384
-#endif
-    static constexpr int THREADS = (NV <= 10) ? FMLP_SIM_THREADS_SMALL : (NV <= 16 ? FMLP_SIM_THREADS_MID : 256);
-    static constexpr int V = R * (NV + 1);                  // values reduced per tile
-    static constexpr int SCRATCH = (V + 3) & ~3;
-#ifndef FMLP_SIM_DEPTH
-#define FMLP_SIM_DEPTH 4
-#endif
-    static constexpr int DEPTH = FMLP_SIM_DEPTH;            // cp.async batches in flight per warp
-    static constexpr int RING = DEPTH * R * 128;            // floats per warp
+    static constexpr int W = FMLP_SIM_W;                                  // compute warps per CTA
+    static constexpr int RT = (NV <= 8) ? FMLP_SIM_RT_SMALL : FMLP_SIM_RT_LARGE;  // rows per thread
+    static constexpr int ROWS = 32 * RT;                                  // rows per tile
+    static constexpr int THREADS = 32 * W;
+    static constexpr int STAGE_BYTES = ROWS * 128;                        // one box: ROWS x 32 floats
+    static constexpr int PV = NV + 1;                                     // partial values per row
 };
 
 __device__ __forceinline__ void fma2(u64& acc, u64 a, u64 b) {
@@ -76,234 +88,221 @@ __device__ __forceinline__ float pair_sum(u64 v) {
     asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     return lo + hi;
 }
-// 128-bit streaming load returned as two packed fp32 pairs
-__device__ __forceinline__ void ldg_pairs(const float* p, u64& a, u64& b) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+__device__ __forceinline__ uint32_t sim_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sim_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void lds_pairs(uint32_t saddr, u64& a, u64& b) {
-    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
+__device__ __forceinline__ void sim_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination.  The .ca form
-// goes through L1, which merges the 32 lanes' 16-byte pieces into 128-byte line fills; with .cg
-// every lane pulled its own 32-byte sector from L2 and the L2->SM traffic doubled (r01 ncu:
-// l1tex__m_xbar2l1tex_read_bytes 456 MB for 225 MB of features, L2 hit rate 51 %).
-#ifndef FMLP_SIM_CPASYNC
-#define FMLP_SIM_CPASYNC "cp.async.ca.shared.global"
-#endif
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const float* g, int src_bytes) {
-    asm volatile(FMLP_SIM_CPASYNC " [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
+__device__ __forceinline__ bool sim_mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sim_mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!sim_mbar_try(bar, parity)) {}
+}
+// 2-D tiled TMA load: box = [ROWS rows][32 columns], 128-byte swizzle; OOB rows / columns read as 0
+__device__ __forceinline__ void sim_tma_load(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(col), "r"(row), "r"(bar) : "memory");
+}
 
-// One stage of the transposed warp reduction: CUR values per lane -> ceil(CUR/2), lanes whose
-// MASK bit is set keep the upper half.
-template <int CUR, int MASK>
-__device__ __forceinline__ void reduce_stage(float* v, int lane) {
-    constexpr int HALF = (CUR + 1) / 2;
-    const bool up = (lane & MASK) != 0;
-#pragma unroll
-    for (int i = 0; i < HALF; ++i) {
-        const float a = v[i];
-        const float b = (i + HALF < CUR) ? v[i + HALF] : 0.f;
-        const float send = up ? a : b;
-        const float keep = up ? b : a;
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
-    }
+// global -> shared bulk copy (SASS UBLKCP); completion is counted in bytes on `bar`
+__device__ __forceinline__ void sim_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-template <int V>
-struct Halving {
-    static constexpr int h0 = (V + 1) / 2, h1 = (h0 + 1) / 2, h2 = (h1 + 1) / 2, h3 = (h2 + 1) / 2,
-                         h4 = (h3 + 1) / 2;  // values per lane after the stages with mask 16, 8, 4, 2, 1
-    // original value index held in slot i of `lane` after all five stages, or -1 for padding
-    __device__ static int index_of(int i, int lane) {
-        int s = i;
-        if (s >= h4) return -1;
-        s += h4 * (lane & 1);         if (s >= h3) return -1;
-        s += h3 * ((lane >> 1) & 1);  if (s >= h2) return -1;
-        s += h2 * ((lane >> 2) & 1);  if (s >= h1) return -1;
-        s += h1 * ((lane >> 3) & 1);  if (s >= h0) return -1;
-        s += h0 * ((lane >> 4) & 1);  if (s >= V) return -1;
-        return s;
-    }
-};
 
-template <int NPAIR, bool FOLD, bool ALIGNED>
+// ---- class-vector table (one CTA per scored class) -------------------------------------------
+// |P[2c]|, |P[2c+1]| (torch.norm: sqrt of the fp32 sum of squares), then the vectors the main kernel
+// multiplies with, element (d, j) at table[((d >> 2) * NV + j) * 4 + (d & 3)], columns D..NG*32 zero.
+__global__ void __launch_bounds__(256) sim_quad_table_kernel(const float* __restrict__ proto, int D, int NG, int fold,
+                                                             int npair, const __grid_constant__ SimArgs a,
+                                                             float* __restrict__ table) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the main kernel may start its prologue now
+    __shared__ float red[2][8];
+    __shared__ float nrm[2];
+    const int q = blockIdx.x;
+    const int c = a.cls[q];
+    const float* p0 = proto + (int64_t)(2 * c) * D;
+    const float* p1 = p0 + D;
+    float s0 = 0.f, s1 = 0.f;
+    for (int d = threadIdx.x; d < D; d += 256) { const float u = p0[d], v = p1[d]; s0 = fmaf(u, u, s0); s1 = fmaf(v, v, s1); }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        nrm[threadIdx.x] = sqrtf(s);
+    }
+    __syncthreads();
+    const int nv = fold ? npair : 2 * npair;
+    for (int d = threadIdx.x; d < NG * 32; d += 256) {
+        const float u = d < D ? p0[d] : 0.f, v = d < D ? p1[d] : 0.f;
+        float* dst = table + ((size_t)(d >> 2) * nv) * 4 + (d & 3);
+        if (fold) {
+            dst[q * 4] = d < D ? __fsub_rn(__fdiv_rn(u, nrm[0]), __fdiv_rn(v, nrm[1])) : 0.f;
+        } else {
+            dst[(2 * q) * 4] = u;
+            dst[(2 * q + 1) * 4] = v;
+        }
+    }
+    if (threadIdx.x < 2) table[(size_t)nv * NG * 32 + 2 * q + threadIdx.x] = nrm[threadIdx.x];
+}
+
+template <int NPAIR, bool FOLD>
 __global__ void __launch_bounds__(SimCfg<NPAIR, FOLD>::THREADS, 1)
-tag_sim_kernel(const __grid_constant__ SimArgs a) {
+tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtensorMap tmap) {
     using Cfg = SimCfg<NPAIR, FOLD>;
-    constexpr int NV = Cfg::NV;
-    constexpr int R = Cfg::R;
-    constexpr int V = Cfg::V;
-    using H = Halving<V>;
-    extern __shared__ __align__(16) float smem[];
-    const int D = a.D, Dpad = a.Dpad;
-    float* sP = smem;                                // [Dpad/128][NV][128]: LDS offsets are immediates
-    float* sNorm = smem + (size_t)NV * Dpad;         // [2*NPAIR] prototype norms (pair order), padded to 4
-    float* sScratch = sNorm + ((2 * NPAIR + 3) & ~3);  // [warps][SCRATCH]
-    float* sRing = sScratch + (size_t)(blockDim.x >> 5) * Cfg::SCRATCH;  // [warps][DEPTH][R][128]
+    constexpr int NV = Cfg::NV, RT = Cfg::RT, W = Cfg::W, ROWS = Cfg::ROWS, PV = Cfg::PV;
+    constexpr int STAGE = Cfg::STAGE_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int S = a.S, D = a.D, NG = a.NG;
+    // [W][S] boxes (1024-byte aligned: the swizzle pattern is a function of the address bits)
+    unsigned char* sRing = smem_raw;
+    float* sP = reinterpret_cast<float*>(sRing + (size_t)W * S * STAGE);   // [NG*8 column quads][NV] float4
+    float* sPart = sP + (size_t)NG * 32 * NV;                              // [W][PV][ROWS] partial sums
+    float* sNorm = sPart + (size_t)W * PV * ROWS;                          // [2*NPAIR] prototype norms, padded to 4
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sNorm + ((2 * NPAIR + 3) & ~3));   // [W][S] ring barriers, then 1 for the table
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
 
-    // ---- producer: one tile of R rows per warp, features through the cp.async ring.  The ring is
-    //      primed BEFORE the prototype prologue so the first DEPTH-1 batches are in flight while the
-    //      norms and the class vectors are staged (the ring is private to the warp and independent of them)
-    const int nchunks = Dpad >> 7;
-    constexpr int DEPTH = Cfg::DEPTH;
-    const int64_t n_tiles = (a.n_total + R - 1) / R;
-    const int64_t tile_stride = (int64_t)gridDim.x * nwarps;
-    const int64_t t_first = (int64_t)blockIdx.x * nwarps + warp;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(sRing + (size_t)warp * Cfg::RING) + lane * 16;
-    // producer cursor: batch = (tile, chunk), runs DEPTH-1 batches ahead of the math.  All address
-    // arithmetic is running pointers / offsets (r01 ncu: a third of the instructions of the first
-    // ring version were IMAD/ISETP/SEL/LEA in this path); only the single ragged tile clamps rows.
-    int64_t t_issue = t_first;
-    int c_issue = 0;
-    uint32_t slot_issue = 0;                                        // byte offset of the ring slot
-    const float* g_tile = a.feat + t_first * R * a.ld_feat + lane * 4;  // row0 of the producer's tile
-    const int64_t g_stride = tile_stride * R * a.ld_feat;
-    const int64_t t_ragged = (a.n_total % R) ? n_tiles - 1 : -1;
+    const int64_t n_tiles = (a.n_total + ROWS - 1) / ROWS;
+    const int my_groups = (NG > warp) ? (NG - warp + W - 1) / W : 0;       // column groups warp, warp+W, ...
+    const uint32_t ring_u32 = sim_smem_u32(sRing + (size_t)warp * S * STAGE);
+    const uint32_t bar_u32 = sim_smem_u32(sBar + warp * S);
+
+    // ---- producer state (lane 0 of each warp): next box = (tile, group) in consumption order
+    int64_t p_tile = blockIdx.x;
+    int p_gi = 0;
+    int p_slot = 0;
     auto issue = [&]() {
-        if (t_issue < n_tiles) {
-            const int col = c_issue * 128 + lane * 4;
-            const int bytes = (ALIGNED || col < D) ? 16 : 0;
-            const float* g = g_tile + (bytes ? c_issue * 128 : 0);
-            if (t_issue != t_ragged) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + r * a.ld_feat, bytes);
-            } else {
-                const int rmax = (int)(a.n_total - 1 - t_issue * R);  // rows past the end re-read the last row
-#pragma unroll
-                for (int r = 0; r < R; ++r) cp_async16(ring_addr + slot_issue + r * 512, g + (r < rmax ? r : rmax) * a.ld_feat, bytes);
-            }
-            if (++c_issue == nchunks) { c_issue = 0; t_issue += tile_stride; g_tile += g_stride; }
+        if (p_tile < n_tiles && my_groups > 0) {
+            const uint32_t bar = bar_u32 + p_slot * 8;
+            sim_mbar_expect_tx(bar, STAGE);                                // OOB parts of a box count as filled
+            sim_tma_load(ring_u32 + p_slot * STAGE, &tmap, (warp + p_gi * W) * 32, (int)(p_tile * ROWS), bar);
+            if (++p_gi == my_groups) { p_gi = 0; p_tile += gridDim.x; }
         }
-        cp_async_commit();  // empty groups keep the wait_group arithmetic uniform
-        slot_issue = (slot_issue + R * 512 == DEPTH * R * 512) ? 0u : slot_issue + R * 512;
+        p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
     };
-#pragma unroll
-    for (int d = 0; d < DEPTH - 1; ++d) issue();
-
-    // ---- prologue: prototype norms, then stage the vectors ----------------------------
-    // |P_j| = sqrt(sum p^2) (torch.norm), one warp per prototype row.
-    for (int j = warp; j < 2 * NPAIR; j += nwarps) {
-        const int prow = 2 * (int)a.cls[j >> 1] + (j & 1);
-        const float* src = a.proto + (int64_t)prow * D;
-        float ss = 0.f;
-        for (int d = lane; d < D; d += 32) { float v = src[d]; ss = fmaf(v, v, ss); }
-        ss = warp_sum(ss);
-        if (lane == 0) sNorm[j] = sqrtf(ss);
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < NV * Dpad; idx += blockDim.x) {
-        const int j = idx / Dpad, d = idx - j * Dpad;
-        float v = 0.f;
-        if (d < D) {
-            if (FOLD) {
-                const int c = a.cls[j];
-                const float p0 = a.proto[(int64_t)(2 * c) * D + d];
-                const float p1 = a.proto[(int64_t)(2 * c + 1) * D + d];
-                v = __fsub_rn(__fdiv_rn(p0, sNorm[2 * j]), __fdiv_rn(p1, sNorm[2 * j + 1]));
-            } else {
-                const int prow = 2 * (int)a.cls[j >> 1] + (j & 1);
-                v = a.proto[(int64_t)prow * D + d];
-            }
+    const uint32_t tbar_u32 = sim_smem_u32(sBar + W * S);
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) sim_mbar_init(bar_u32 + s * 8, 1);
+        if (warp == 0) sim_mbar_init(tbar_u32, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < S; ++s) issue();     // the ring fills while the table kernel finishes
+        if (warp == 0) {
+            // the class vectors come from the table kernel this launch programmatically depends on
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            const uint32_t bytes = (uint32_t)((NG * 32 * NV + ((2 * NPAIR + 3) & ~3)) * sizeof(float));
+            sim_mbar_expect_tx(tbar_u32, bytes);
+            // sP, sPart, sNorm are laid out so that table = [sP | norms] lands with two copies
+            sim_bulk_g2s(sim_smem_u32(sP), a.table, (uint32_t)(NG * 32 * NV * sizeof(float)), tbar_u32);
+            sim_bulk_g2s(sim_smem_u32(sNorm), a.table + (size_t)NG * 32 * NV, (uint32_t)(((2 * NPAIR + 3) & ~3) * sizeof(float)), tbar_u32);
         }
-        sP[((d >> 7) * NV + j) * 128 + (d & 127)] = v;
     }
-    __syncthreads();
+    __syncthreads();                              // barrier inits are visible to every waiter
+    sim_mbar_wait(tbar_u32, 0);
 
-    // where the values this lane ends up with after the transposed reduction belong
-    int out_idx[H::h4];
-#pragma unroll
-    for (int i = 0; i < H::h4; ++i) out_idx[i] = H::index_of(i, lane);
-    float* scratch = sScratch + warp * Cfg::SCRATCH;
-    const uint32_t sP_addr = (uint32_t)__cvta_generic_to_shared(sP) + lane * 16;
+    // lane's row inside a box: 128 bytes per row, 16-byte chunk k of row r sits at chunk k ^ (r & 7)
+    const uint32_t row_off = (uint32_t)lane * 128u + ((uint32_t)(lane & 7) << 4);
+    int slot = 0;
+    uint32_t parity = 0;
 
-    uint32_t slot = 0;  // byte offset of the consumer's ring slot
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        u64 acc[RT][PV];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int j = 0; j < PV; ++j) acc[r][j] = 0ull;
 
-    for (int64_t t = t_first; t < n_tiles; t += tile_stride) {
-        const int64_t row0 = t * R;
-        u64 acc[R][NV];
-        u64 nrm[R];
+        for (int gi = 0; gi < my_groups; ++gi) {
+            sim_mbar_wait(bar_u32 + slot * 8, parity);
+            const unsigned char* box = sRing + ((size_t)warp * S + slot) * STAGE;
+            const ulonglong2* pv = reinterpret_cast<const ulonglong2*>(sP) + (size_t)(warp + gi * W) * 8 * NV;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            nrm[r] = 0ull;
+            for (int k = 0; k < 8; ++k) {
+                ulonglong2 f[RT];
 #pragma unroll
-            for (int j = 0; j < NV; ++j) acc[r][j] = 0ull;
-        }
-        for (int c = 0; c < nchunks; ++c) {
-            issue();
-            cp_async_wait<DEPTH - 1>();  // the batch issued DEPTH-1 calls ago has landed
-            u64 f0[R], f1[R];
+                for (int r = 0; r < RT; ++r)
+                    f[r] = *reinterpret_cast<const ulonglong2*>(box + ((row_off ^ (uint32_t)(k << 4)) + r * 4096));
+                // vectors in groups of JB: all .x products of a group before any .y product, so the two
+                // FFMA2 that hit one accumulator are RT*JB - 1 independent FFMA2 apart (4-cycle FMA latency)
+                // and only JB class-vector quads are live at a time
+                constexpr int JB = 4;
 #pragma unroll
-            for (int r = 0; r < R; ++r) lds_pairs(ring_addr + slot + r * 512, f0[r], f1[r]);
-            slot = (slot + R * 512 == DEPTH * R * 512) ? 0u : slot + R * 512;
-            const uint32_t base = sP_addr + (uint32_t)c * (NV * 512u);
-            // two prototype vectors per step and the f0 products of all of them before any f1
-            // product: the two FFMA2 that hit the same accumulator are 2R-1 independent FFMA2 apart
-            // (back to back they stalled on the 4-cycle FMA latency: "wait" was the top stall reason)
+                for (int j0 = 0; j0 < NV; j0 += JB) {
+                    ulonglong2 p[JB];
 #pragma unroll
-            for (int j = 0; j < NV; j += 2) {
-                u64 p0, p1, q0 = 0ull, q1 = 0ull;
-                lds_pairs(base + j * 512, p0, p1);
-                if (j + 1 < NV) lds_pairs(base + (j + 1) * 512, q0, q1);
+                    for (int j = 0; j < JB; ++j)
+                        if (j0 + j < NV) p[j] = pv[k * NV + j0 + j];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    fma2(acc[r][j], f0[r], p0);
-                    if (j + 1 < NV) fma2(acc[r][j + 1], f0[r], q0);
+                    for (int j = 0; j < JB; ++j)
+                        if (j0 + j < NV)
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) fma2(acc[r][j0 + j], f[r].x, p[j].x);
+#pragma unroll
+                    for (int j = 0; j < JB; ++j)
+                        if (j0 + j < NV)
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) fma2(acc[r][j0 + j], f[r].y, p[j].y);
                 }
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    fma2(acc[r][j], f1[r], p1);
-                    if (j + 1 < NV) fma2(acc[r][j + 1], f1[r], q1);
-                }
+                for (int r = 0; r < RT; ++r) fma2(acc[r][NV], f[r].x, f[r].x);
+#pragma unroll
+                for (int r = 0; r < RT; ++r) fma2(acc[r][NV], f[r].y, f[r].y);
             }
-#pragma unroll
-            for (int r = 0; r < R; ++r) fma2(nrm[r], f0[r], f0[r]);
-#pragma unroll
-            for (int r = 0; r < R; ++r) fma2(nrm[r], f1[r], f1[r]);
+            __syncwarp();                       // every lane is done reading the box
+            if (lane == 0) issue();             // refill it (same slot: the producer cursor trails by S)
+            if (++slot == S) { slot = 0; parity ^= 1u; }
         }
 
-        // ---- combine the 32 lane partials (transposed reduction) ------------------------
-        float v[V];
+        // ---- the W warps' partial sums meet in shared memory --------------------------------
+        __syncthreads();                        // the previous tile's epilogue reads are done
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
-            for (int j = 0; j < NV; ++j) v[r * (NV + 1) + j] = pair_sum(acc[r][j]);
-            v[r * (NV + 1) + NV] = pair_sum(nrm[r]);
-        }
-        reduce_stage<V, 16>(v, lane);
-        reduce_stage<H::h0, 8>(v, lane);
-        reduce_stage<H::h1, 4>(v, lane);
-        reduce_stage<H::h2, 2>(v, lane);
-        reduce_stage<H::h3, 1>(v, lane);
-        __syncwarp();  // previous tile's epilogue reads are done
-#pragma unroll
-        for (int i = 0; i < H::h4; ++i)
-            if (out_idx[i] >= 0) scratch[out_idx[i]] = v[i];
-        __syncwarp();
+            for (int j = 0; j < PV; ++j) sPart[(warp * PV + j) * ROWS + r * 32 + lane] = pair_sum(acc[r][j]);
+        __syncthreads();
 
-        // ---- epilogue: one lane per (row, class); reference op order (norm product,
-        //      reciprocal, multiply, subtract)
-        for (int e = lane; e < R * NPAIR; e += 32) {
-            const int r = e / NPAIR, q = e - r * NPAIR;
+        // ---- epilogue: thread -> (row, class subset); reference op order -------------------
+        const int64_t row0 = tile * ROWS;
+        for (int e = threadIdx.x; e < ROWS * NPAIR; e += Cfg::THREADS) {
+            const int q = e / ROWS, r = e - q * ROWS;
             const int64_t row = row0 + r;
             if (row < a.n_total) {
                 const int c = a.cls[q];
                 const int s = find_segment(a.seg.rows, a.seg.S, row);
                 if ((a.seg.mask_a[s] >> c) & 1u) {
-                    const float* rv = scratch + r * (NV + 1);
-                    const float nf = sqrtf(rv[NV]);
+                    float ff = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {            // fixed warp order: deterministic
+                        const float* part = sPart + (size_t)w * PV * ROWS + r;
+                        ff += part[NV * ROWS];
+                        if (FOLD) {
+                            d0 += part[q * ROWS];
+                        } else {
+                            d0 += part[(2 * q) * ROWS];
+                            d1 += part[(2 * q + 1) * ROWS];
+                        }
+                    }
+                    const float nf = sqrtf(ff);
                     float out;
                     if (FOLD) {
-                        out = __fmul_rn(rv[q], __frcp_rn(nf));
+                        out = __fmul_rn(d0, __frcp_rn(nf));
                     } else {
-                        const float c0 = __fmul_rn(rv[2 * q], __frcp_rn(__fmul_rn(nf, sNorm[2 * q])));
-                        const float c1 = __fmul_rn(rv[2 * q + 1], __frcp_rn(__fmul_rn(nf, sNorm[2 * q + 1])));
+                        const float c0 = __fmul_rn(d0, __frcp_rn(__fmul_rn(nf, sNorm[2 * q])));
+                        const float c1 = __fmul_rn(d1, __frcp_rn(__fmul_rn(nf, sNorm[2 * q + 1])));
                         out = __fsub_rn(c0, c1);
                     }
                     a.sim[(int64_t)c * a.ld_sim + row] = out;
@@ -313,38 +312,95 @@ tag_sim_kernel(const __grid_constant__ SimArgs a) {
     }
 }
 
-template <int NPAIR, bool FOLD, bool ALIGNED>
-static int launch_sim_inst(const SimArgs& a, cudaStream_t st) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*SimTensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SimTensorMapEncodeFn sim_tensor_map_encoder() {
+    static SimTensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<SimTensorMapEncodeFn>(p);
+    }
+    return fn;
+}
+
+static bool sim_use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FMLP_SIM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
+static size_t sim_table_floats(int nv, int npair, int NG) { return (size_t)NG * 32 * nv + ((2 * npair + 3) & ~3); }
+
+struct SimFeat {
+    const float* feat;
+    int64_t ld_feat;
+};
+
+template <int NPAIR, bool FOLD>
+static int launch_sim(SimArgs& a, const SimFeat& ft, cudaStream_t st) {
     using Cfg = SimCfg<NPAIR, FOLD>;
-    const int warps = Cfg::THREADS / 32;
-    const size_t smem = ((size_t)Cfg::NV * a.Dpad + ((2 * NPAIR + 3) & ~3) + (size_t)warps * (Cfg::SCRATCH + Cfg::RING)) * sizeof(float);
-    if (smem > 227u * 1024u) return FMLP_ERR_UNSUPPORTED;
-    auto kern = tag_sim_kernel<NPAIR, FOLD, ALIGNED>;
+    const size_t fixed = ((size_t)a.NG * 32 * Cfg::NV + (size_t)Cfg::W * Cfg::PV * Cfg::ROWS + ((2 * NPAIR + 3) & ~3)) * sizeof(float);
+    const size_t budget = 227u * 1024u;
+    static int max_stages = 0;
+    if (max_stages == 0) {
+        max_stages = 8;
+        if (const char* e = getenv("FMLP_SIM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 16) max_stages = v; }
+    }
+    int S = max_stages;
+    auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + (size_t)Cfg::W * s * sizeof(uint64_t); };
+    while (S > 2 && smem_of(S) > budget) --S;
+    const size_t smem = smem_of(S);
+    if (smem > budget) return FMLP_ERR_UNSUPPORTED;
+    a.S = S;
+    auto kern = tag_sim_kernel<NPAIR, FOLD>;
     static size_t configured = 0;  // per template instance
     if (smem > 48u * 1024u && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
+    SimTensorMapEncodeFn enc = sim_tensor_map_encoder();
+    if (!enc) return FMLP_ERR_UNSUPPORTED;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)a.n_total};
+    cuuint64_t strides[1] = {(cuuint64_t)ft.ld_feat * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)Cfg::ROWS};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ft.feat), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FMLP_ERR_UNSUPPORTED;
     const int sms = sm_count();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
-    const int64_t n_tiles = (a.n_total + Cfg::R - 1) / Cfg::R;
-    int64_t blocks = (n_tiles + warps - 1) / warps;
-    if (blocks > sms) blocks = sms;  // persistent: one CTA per SM
-    if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, Cfg::THREADS, smem, st>>>(a);
-    return launch_status();
-}
-
-template <int NPAIR, bool FOLD>
-static int launch_sim(const SimArgs& a, cudaStream_t st) {
-    return (a.D % 128 == 0) ? launch_sim_inst<NPAIR, FOLD, true>(a, st) : launch_sim_inst<NPAIR, FOLD, false>(a, st);
+    sim_quad_table_kernel<<<NPAIR, 256, 0, st>>>(a.proto, a.D, a.NG, FOLD ? 1 : 0, NPAIR, a, const_cast<float*>(a.table));
+    int rc = launch_status();
+    if (rc != FMLP_OK) return rc;
+    const int64_t n_tiles = (a.n_total + Cfg::ROWS - 1) / Cfg::ROWS;
+    const int64_t blocks = n_tiles < sms ? n_tiles : sms;     // persistent: one CTA per SM, tiles round-robin
+    // programmatic dependent launch: the main kernel's barrier setup and first feature boxes overlap
+    // the table kernel; it waits (griddepcontrol.wait) right before it copies the table
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = sim_use_pdl() ? 1 : 0;
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, tmap);
+    return e == cudaSuccess ? launch_status() : (int)e;
 }
 
 template <bool FOLD>
-static int dispatch_sim(int npair, const SimArgs& a, cudaStream_t st) {
+static int dispatch_sim(int npair, SimArgs& a, const SimFeat& ft, cudaStream_t st) {
     switch (npair) {
-#define FMLP_SIM_CASE(N) case N: return launch_sim<N, FOLD>(a, st);
+#define FMLP_SIM_CASE(N) case N: return launch_sim<N, FOLD>(a, ft, st);
         FMLP_SIM_CASE(1) FMLP_SIM_CASE(2) FMLP_SIM_CASE(3) FMLP_SIM_CASE(4)
         FMLP_SIM_CASE(5) FMLP_SIM_CASE(6) FMLP_SIM_CASE(7) FMLP_SIM_CASE(8)
         FMLP_SIM_CASE(9) FMLP_SIM_CASE(10) FMLP_SIM_CASE(11) FMLP_SIM_CASE(12)
@@ -358,11 +414,20 @@ static int dispatch_sim(int npair, const SimArgs& a, cudaStream_t st) {
 
 using namespace fmlp;
 
+extern "C" size_t fmlp_tag_sim_ws_bytes(int C, int D) {
+    if (C < 1 || C > FMLP_MAX_CLASSES || D < 1) return 0;
+    const int n = C < 16 ? C : 16;            // at most 16 classes per launch, pair mode = 2 vectors each
+    return (sim_table_floats(2 * n, n, (D + 31) >> 5) * sizeof(float) + 15) & ~(size_t)15;
+}
+
 extern "C" int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const float* proto, int C,
                                 int S, const int64_t* seg_rows, const uint32_t* seg_missing,
-                                float* sim, int64_t ld_sim, int mode, fmlp_stream_t stream) {
+                                float* sim, int64_t ld_sim, int mode, void* ws, size_t ws_bytes,
+                                fmlp_stream_t stream) {
     if (!feat || !proto || !sim || !seg_missing || C < 1 || C > FMLP_MAX_CLASSES || D < 4)
         return FMLP_ERR_BAD_ARG;
+    if (!ws || !aligned16(ws)) return FMLP_ERR_BAD_ARG;
+    if (ws_bytes < fmlp_tag_sim_ws_bytes(C, D)) return FMLP_ERR_WORKSPACE;
     if ((D & 3) || (ld_feat & 3) || ld_feat < D || !aligned16(feat)) return FMLP_ERR_UNSUPPORTED;
     if (mode != FMLP_SIM_PAIR && mode != FMLP_SIM_FOLDED) return FMLP_ERR_BAD_ARG;
     SimArgs a;
@@ -371,6 +436,7 @@ extern "C" int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const
     a.n_total = seg_rows[S];
     if (ld_sim < a.n_total) return FMLP_ERR_BAD_ARG;
     if (a.n_total == 0) return FMLP_OK;
+    if (a.n_total > 0x7fffffffll) return FMLP_ERR_UNSUPPORTED;    // TMA row coordinates are int32
     uint32_t uni = 0;
     for (int s = 0; s < S; ++s) uni |= seg_missing[s];
     if (C < 32) uni &= (1u << C) - 1u;
@@ -379,8 +445,9 @@ extern "C" int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const
     for (int c = 0; c < C; ++c)
         if ((uni >> c) & 1u) a.cls[npair++] = (int8_t)c;
     if (npair == 0) return FMLP_OK;
-    a.feat = feat; a.proto = proto; a.sim = sim; a.ld_feat = ld_feat; a.ld_sim = ld_sim;
-    a.D = D; a.Dpad = (D + 127) & ~127; a.C = C;
+    a.proto = proto; a.table = static_cast<const float*>(ws); a.sim = sim; a.ld_sim = ld_sim;
+    a.D = D; a.NG = (D + 31) >> 5; a.C = C; a.S = 0;
+    const SimFeat ft = {feat, ld_feat};
     cudaStream_t st = (cudaStream_t)stream;
     // More than 16 classes in one launch: split the class set (features are re-read per group).
     if (npair > 16) {
@@ -388,10 +455,10 @@ extern "C" int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const
         for (int base = 0; base < npair; base += 16) {
             const int n = (npair - base) < 16 ? (npair - base) : 16;
             for (int q = 0; q < 16; ++q) b.cls[q] = q < n ? a.cls[base + q] : 0;
-            rc = (mode == FMLP_SIM_FOLDED) ? dispatch_sim<true>(n, b, st) : dispatch_sim<false>(n, b, st);
+            rc = (mode == FMLP_SIM_FOLDED) ? dispatch_sim<true>(n, b, ft, st) : dispatch_sim<false>(n, b, ft, st);
             if (rc != FMLP_OK) return rc;
         }
         return FMLP_OK;
     }
-    return (mode == FMLP_SIM_FOLDED) ? dispatch_sim<true>(npair, a, st) : dispatch_sim<false>(npair, a, st);
+    return (mode == FMLP_SIM_FOLDED) ? dispatch_sim<true>(npair, a, ft, st) : dispatch_sim<false>(npair, a, ft, st);
 }

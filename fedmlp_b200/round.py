@@ -64,6 +64,7 @@ class _Plan:
         self.tcnt = torch.zeros(S, C, dtype=i32, device=dev)
         self.glob = torch.empty(P, dtype=f32, device=dev)
         with torch.cuda.device(dev):
+            self.ws_sim = torch.empty(max(lib.fmlp_tag_sim_ws_bytes(C, D), 256), dtype=torch.uint8, device=dev)
             self.ws_select = torch.empty(max(lib.fmlp_tag_select_ws_bytes(S, C, self.cap), 256), dtype=torch.uint8, device=dev)
             self.ws_loss = torch.empty(max(lib.fmlp_loss_ws_bytes(N, C), 256), dtype=torch.uint8, device=dev)
             self.ws_proto = torch.empty(max(lib.fmlp_proto_ws_bytes(N, D, C, S), 256), dtype=torch.uint8, device=dev)
@@ -192,7 +193,8 @@ class ClientShard:
                         proto_stage(side_stream)
                     aggregate_stage(side_stream)
             check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
-                                       tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], st), "fmlp_tag_sim_f32")
+                                       tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], pl.ws_sim.data_ptr(),
+                                       pl.ws_sim.numel(), st), "fmlp_tag_sim_f32")
             mark("sim")
             check(lib.fmlp_tag_select(tg.sim.data_ptr(), tg.sim.shape[1], tg.tag.data_ptr(), tg.tag.shape[1], C, S,
                                       pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),

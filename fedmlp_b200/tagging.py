@@ -49,6 +49,7 @@ def tag_similarity(features, prototype, missing_classes, seg_rows=None, out=None
     lib = cabi.lib()
     with torch.cuda.device(dev):
         st = cabi.stream_ptr(dev)
+        ws = workspace("sim", lib.fmlp_tag_sim_ws_bytes(C, D), dev)      # class-vector table of the pre-kernel
         for s0 in range(0, S, cabi.MAX_SEGMENTS):
             s1 = min(S, s0 + cabi.MAX_SEGMENTS)
             r0 = seg_rows[s0]
@@ -56,7 +57,7 @@ def tag_similarity(features, prototype, missing_classes, seg_rows=None, out=None
             cabi.check(lib.fmlp_tag_sim_f32(
                 features.data_ptr() + 4 * r0 * D, D, D, prototype.data_ptr(), C, s1 - s0,
                 cabi.i64_array(rows), cabi.u32_array([cabi.class_mask(m) for m in missing_classes[s0:s1]]),
-                out.data_ptr() + 4 * r0, N, SIM_MODES[mode], st), "fmlp_tag_sim_f32")
+                out.data_ptr() + 4 * r0, N, SIM_MODES[mode], ws.data_ptr(), ws.numel(), st), "fmlp_tag_sim_f32")
     return out
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FMLP_ABI_VERSION 2 /* 2: fmlp_fedavg_allreduce_f32 takes n_chunks; pool_tag, sim_table, eval, adam entry points */
+#define FMLP_ABI_VERSION 3 /* 3: fmlp_tag_sim_f32 takes a workspace (class-vector table); 2: allreduce n_chunks, pool_tag, eval, adam */
 #define FMLP_MAX_CLASSES 32   /* class bit masks are uint32_t                        */
 #define FMLP_MAX_SEGMENTS 64  /* segments (clients) per launch                        */
 #define FMLP_MAX_CLIENTS 64   /* client buffers folded per fedavg launch              */
@@ -191,11 +191,16 @@ int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, const float*
  *           left untouched
  *   mode    FMLP_SIM_PAIR: two cosines then subtract (op order of the reference)
  *           FMLP_SIM_FOLDED: one dot against q_c = P[2c]/|P[2c]| - P[2c+1]/|P[2c+1]|
- *           (half the FMAs; differs from PAIR by O(1e-7), inside the north_star waiver)    */
+ *           (half the FMAs; differs from PAIR by O(1e-7), inside the north_star waiver)
+ *   ws      fmlp_tag_sim_ws_bytes(C, D) bytes, 16-byte aligned: the class-vector table a small
+ *           pre-kernel builds once per call (prototype norms, folded vectors) and every CTA of
+ *           the streaming kernel copies; the two launches are chained by a programmatic
+ *           dependent launch                                                                */
 enum { FMLP_SIM_PAIR = 0, FMLP_SIM_FOLDED = 1 };
+size_t fmlp_tag_sim_ws_bytes(int C, int D);
 int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const float* proto, int C,
                      int S, const int64_t* seg_rows, const uint32_t* seg_missing, float* sim,
-                     int64_t ld_sim, int mode, fmlp_stream_t stream);
+                     int64_t ld_sim, int mode, void* ws, size_t ws_bytes, fmlp_stream_t stream);
 
 /* ------------------------------------------------------------------ K3 fused into feature extraction
  * (SURVEY §8f.1).  The reference's tagging pass keeps, per batch, only the pooled feature of the

@@ -33,12 +33,14 @@ def test_argument_validation_without_gpu(lib):
     # null pointers / bad sizes are rejected before any CUDA call
     assert lib.fmlp_fedavg_flat_f32(None, None, 1, 10, 1.0, 1, None, None) == -1
     assert lib.fmlp_fedavg_flat_f32(c.ptr_array([16]), c.f32_array([1.0]), 65, 10, 1.0, 1, 16, None) == -1
-    assert lib.fmlp_tag_sim_f32(None, 4, 4, None, 5, 1, None, None, None, 0, 0, None) == -1
+    assert lib.fmlp_tag_sim_f32(None, 4, 4, None, 5, 1, None, None, None, 0, 0, None, 0, None) == -1
     assert lib.fmlp_loss_stage2_f32(None, None, None, None, 1, 5, 0, None, None, None, 0, None) == -1
     # misaligned / unsupported shapes
     rows = c.i64_array([0, 8])
     m = c.u32_array([1])
-    assert lib.fmlp_tag_sim_f32(16, 6, 6, 16, 5, 1, rows, m, 16, 8, 0, None) == -2        # D % 4 != 0
+    assert lib.fmlp_tag_sim_f32(16, 6, 6, 16, 5, 1, rows, m, 16, 8, 0, 16, 1 << 20, None) == -2        # D % 4 != 0
+    assert lib.fmlp_tag_sim_f32(16, 8, 8, 16, 5, 1, rows, m, 16, 8, 0, 16, 8, None) == -3              # workspace too small
+    assert lib.fmlp_tag_sim_ws_bytes(5, 1024) >= (2 * 5 * 1024 + 10) * 4
     assert lib.fmlp_tag_select_ws_bytes(8, 5, 100) == 8 * 5 * 2 * 100 * 8
     assert lib.fmlp_loss_ws_bytes(32, 5) >= 4 * 2048 * 4
 
