@@ -23,7 +23,7 @@ LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libfedmlp_b200.so"
 OBJ_DIR = PKG / "build"
 
-SOURCES = ["cabi.cu", "adam.cu", "fedavg.cu", "fedavg_allreduce.cu", "proto.cu", "tag_sim.cu", "pool_tag.cu", "tag_select.cu", "loss.cu", "eval.cu"]
+SOURCES = ["cabi.cu", "adam.cu", "fedavg.cu", "fedavg_allreduce.cu", "fedavg_allreduce_q.cu", "proto.cu", "tag_sim.cu", "pool_tag.cu", "tag_select.cu", "loss.cu", "eval.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 # keep the statically linked CUDA runtime private to this library (torch ships its own libcudart)

@@ -143,6 +143,154 @@ class FusedFedAvgAllReduce:
         return self.result[:self.P]
 
 
+class QueuedAggregation:
+    """Round-2 aggregation exchange (csrc/fedavg_allreduce_q.cu): local K-way weighted fold + all-reduce of
+    [P parameters | T tail floats | M fp64 scalars] in ONE non-cooperative work-queue kernel per rank.  The
+    reduction goes through the NVSwitch (multimem.ld_reduce / multimem.st) when torch's symmetric memory
+    exposes a multicast mapping, otherwise by peer loads in rank order + peer stores.  Symmetric buffers are
+    allocated and exchanged once; every call is a single ordinary launch on the current stream (CUDA-graph
+    capturable, overlaps kernels of other streams).  Collective: all ranks call it with the same shapes."""
+
+    FLAG_WORDS = 512      # FMLP_AR_FLAG_WORDS
+
+    def __init__(self, P: int, T: int = 0, M: int = 0, group=None, device=None, n_chunks=None, max_ctas=None,
+                 use_multicast=None):
+        import os
+
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("QueuedAggregation supports up to 8 ranks (one NVSwitch domain)")
+        if P % 4 or T % 4:
+            raise ValueError("P and T must be multiples of 4 (16-byte padded buffers)")
+        self.P, self.T, self.M = int(P), int(T), int(M)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = cabi.lib()
+        n = int(lib.fmlp_fedavg_allreduce_q_buffer_floats(self.P, self.T, self.M))
+        if n_chunks is None:
+            n_chunks = int(os.environ.get("FMLP_ARQ_CHUNKS", "4"))
+        self.n_chunks = max(1, min(16, int(n_chunks)))
+        self.max_ctas = int(os.environ.get("FMLP_ARQ_CTAS", "0")) if max_ctas is None else int(max_ctas)
+        self.partial = symm.empty(n, dtype=torch.float32, device=self.device)
+        self.result = symm.empty(n, dtype=torch.float32, device=self.device)
+        self.flags = symm.empty(self.FLAG_WORDS, dtype=torch.int32, device=self.device)
+        self.partial.zero_(); self.result.zero_(); self.flags.zero_()
+        hp = symm.rendezvous(self.partial, self.group)
+        hr = symm.rendezvous(self.result, self.group)
+        hf = symm.rendezvous(self.flags, self.group)
+        self._handles = (hp, hr, hf)
+
+        def peer_ptrs(h, t):
+            # buffer_ptrs are the bases of the allocation blocks; the tensor may sit at an offset inside its block
+            off = t.data_ptr() - int(h.buffer_ptrs[self.rank])
+            return [int(b) + off for b in h.buffer_ptrs], off
+
+        pp, off_p = peer_ptrs(hp, self.partial)
+        rp, off_r = peer_ptrs(hr, self.result)
+        fp, _ = peer_ptrs(hf, self.flags)
+        self.partial_ptrs, self.result_ptrs, self.flag_ptrs = cabi.ptr_array(pp), cabi.ptr_array(rp), cabi.ptr_array(fp)
+        if use_multicast is None:
+            use_multicast = os.environ.get("FMLP_ARQ_MULTICAST", "1") != "0"
+        self.mc_partial = self.mc_result = 0
+        if use_multicast and self.world > 1:
+            try:
+                mp_, mr_ = int(hp.multicast_ptr), int(hr.multicast_ptr)
+                if mp_ and mr_:
+                    self.mc_partial, self.mc_result = mp_ + off_p, mr_ + off_r
+            except Exception:      # no multicast support on this system: peer-to-peer path
+                self.mc_partial = self.mc_result = 0
+        # every rank must take the same path (the flags protocol is the same, the data path is not)
+        ok = torch.tensor([1 if self.mc_partial else 0], dtype=torch.int32, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.mc_partial = self.mc_result = 0
+        self.nvls = bool(self.mc_partial)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.device)   # per-rank call counter
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)          # every rank's flags are zero before anyone signals
+
+    @property
+    def path(self) -> str:
+        return "nvls multimem" if self.nvls else "peer-to-peer pull/push"
+
+    def __call__(self, local_bufs, weights_normalised, tail_bufs=None, tail_f64=None):
+        """local_bufs: K contiguous fp32 [P] tensors; tail_bufs: K fp32 [T] tensors (T > 0); tail_f64: device
+        float64 [M] (M > 0).  Returns (params [P], tail [T], f64 [M]) — views of this rank's symmetric result
+        buffer, overwritten by the next call."""
+        K = len(local_bufs)
+        if not 1 <= K <= cabi.MAX_CLIENTS:
+            raise ValueError(f"1..{cabi.MAX_CLIENTS} clients per rank")
+        cabi.require_cuda(*local_bufs)
+        for b in local_bufs:
+            if b.numel() != self.P or b.dtype != torch.float32 or not b.is_contiguous():
+                raise ValueError("client buffers must be contiguous float32 of length P")
+        tails = None
+        if self.T:
+            if tail_bufs is None or len(tail_bufs) != K:
+                raise ValueError("one tail vector per client")
+            for b in tail_bufs:
+                if b.numel() != self.T or b.dtype != torch.float32 or not b.is_contiguous() or not b.is_cuda:
+                    raise ValueError("tail vectors must be contiguous float32 CUDA tensors of length T")
+            tails = cabi.ptr_array([b.data_ptr() for b in tail_bufs])
+        if self.M and (tail_f64 is None or tail_f64.numel() != self.M or tail_f64.dtype != torch.float64 or not tail_f64.is_cuda):
+            raise ValueError("tail_f64 must be a float64 CUDA tensor of length M")
+        with torch.cuda.device(self.device):
+            cabi.check(cabi.lib().fmlp_fedavg_allreduce_q_f32(
+                cabi.ptr_array([b.data_ptr() for b in local_bufs]), tails, cabi.f32_array(weights_normalised), K,
+                self.P, self.T, tail_f64.data_ptr() if self.M else None, self.M,
+                self.partial_ptrs, self.result_ptrs, self.flag_ptrs, self.mc_partial or None, self.mc_result or None,
+                self.n_chunks, self.rank, self.world, self.epoch_dev.data_ptr(), self.max_ctas,
+                cabi.stream_ptr(self.device)), "fmlp_fedavg_allreduce_q_f32")
+        r = self.result
+        f64 = r[self.P + self.T:self.P + self.T + 2 * self.M].view(torch.float64) if self.M else None
+        return r[:self.P], (r[self.P:self.P + self.T] if self.T else None), f64
+
+
+class FedMLPAggregation:
+    """The whole server aggregation of a FedMLP round (main.py:218-234) for the clients of this rank, across
+    ranks, in three launches: tail pack -> QueuedAggregation -> finalize.  Produces, identically on every rank,
+    the FedAvg parameters (utils/FedAvg.py:7-14), the aggregated prototypes (FedAvg_proto, :72-93), tao
+    (FedAvg_tao, :51-70, float64) and the int64 BatchNorm counters as float32 (FedAvg.py:13)."""
+
+    def __init__(self, P: int, C: int, D: int, J: int = 0, group=None, device=None, **kw):
+        self.C, self.D, self.J = int(C), int(D), int(J)
+        self.T = 2 * self.C * self.D
+        self.M = 3 * self.C + self.J
+        self.exchange = QueuedAggregation(P, self.T, self.M, group=group, device=device, **kw)
+        dev = self.exchange.device
+        self.tail_local = torch.zeros(self.M, dtype=torch.float64, device=dev)
+        self.proto = torch.empty(2 * self.C, self.D, dtype=torch.float32, device=dev)
+        self.tao = torch.empty(self.C, dtype=torch.float64, device=dev)
+        self.counters = torch.empty(max(self.J, 1), dtype=torch.float32, device=dev)
+
+    def __call__(self, client_flats, client_protos, tcnt, weights, rows, active, missing, total_weight, counters=None):
+        """client_flats: K fp32 [P]; client_protos: K fp32 [2C, D] (rows of classes the client does not annotate
+        are zero, as utils/local_training.py:973-1002 leaves them); tcnt: int32 [K, C] confident counts;
+        weights / rows: K client weights (dict_len) and row counts; active / missing: K class lists;
+        total_weight: sum of weights over ALL ranks; counters: K int64 [J] tensors or None."""
+        ex = self.exchange
+        K = len(client_flats)
+        lib = cabi.lib()
+        dev = ex.device
+        wn = [float(w) / float(total_weight) for w in weights]
+        with torch.cuda.device(dev):
+            st = cabi.stream_ptr(dev)
+            cabi.check(lib.fmlp_agg_tail_pack_f64(
+                tcnt.data_ptr() if tcnt is not None else None, K, self.C, cabi.f64_array(weights), cabi.i64_array(rows),
+                cabi.u32_array([cabi.class_mask(a) for a in active]), cabi.u32_array([cabi.class_mask(m) for m in missing]),
+                cabi.ptr_array([c.data_ptr() for c in counters]) if self.J else None, self.J,
+                self.tail_local.data_ptr(), st), "fmlp_agg_tail_pack_f64")
+            params, psum, f64 = ex(client_flats, wn, tail_bufs=[p.reshape(-1) for p in client_protos], tail_f64=self.tail_local)
+            cabi.check(lib.fmlp_agg_finalize_f32(psum.data_ptr(), f64.data_ptr(), self.C, self.D, self.J, float(total_weight),
+                                                 self.proto.data_ptr(), self.tao.data_ptr(),
+                                                 self.counters.data_ptr() if self.J else None, st), "fmlp_agg_finalize_f32")
+        return params, self.proto, self.tao, (self.counters[:self.J] if self.J else None)
+
+
 def FedAvg_distributed(w_local, dict_len_local, group=None, total_weight=None, local_reduce=None):
     """Distributed drop-in for FedAvg(w, dict_len) (reference utils/FedAvg.py:7-14): every rank
     passes the state_dicts and weights of ITS clients; all ranks get the same averaged dict

@@ -38,6 +38,9 @@ class RoundResult:
     protos: PrototypeResult         # per-client prototypes / counts / t counts
     global_flat: torch.Tensor       # [P] aggregated parameters
     events: dict = field(default_factory=dict)
+    proto_glob: torch.Tensor = None  # [2C, D] aggregated prototypes (FedAvg_proto), when the tails are aggregated
+    tao: torch.Tensor = None         # [C] float64 (FedAvg_tao)
+    counters: torch.Tensor = None    # [J] float32 aggregated int64 BatchNorm counters
 
 
 class _Plan:
@@ -63,6 +66,13 @@ class _Plan:
         self.cnt = torch.empty(S, 2 * C, dtype=i32, device=dev)
         self.tcnt = torch.zeros(S, C, dtype=i32, device=dev)
         self.glob = torch.empty(P, dtype=f32, device=dev)
+        # aggregation tails (FedAvg_proto / FedAvg_tao / int64 counters, main.py:218-234)
+        self.proto_glob = torch.empty(2 * C, D, dtype=f32, device=dev)
+        self.tao = torch.empty(C, dtype=torch.float64, device=dev)
+        self.tail = torch.zeros(3 * C + 1024, dtype=torch.float64, device=dev)
+        self.counters = torch.empty(1024, dtype=f32, device=dev)
+        self.class_active = cabi.u64_array([sum(1 << k for k in range(S) if c in shard.active[k]) for c in range(C)])
+        self.sizes = cabi.i64_array(shard.sizes)
         with torch.cuda.device(dev):
             self.ws_sim = torch.empty(max(lib.fmlp_tag_sim_ws_bytes(C, D), 256), dtype=torch.uint8, device=dev)
             self.ws_select = torch.empty(max(lib.fmlp_tag_select_ws_bytes(S, C, self.cap), 256), dtype=torch.uint8, device=dev)
@@ -99,6 +109,7 @@ class ClientShard:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.clean_frac, self.noise_frac, self.L, self.U = float(clean_frac), float(noise_frac), float(L), float(U)
         self.sim_mode = sim_mode
+        self.loss_variant = cabi.LOSS2_SUP      # cabi.LOSS2_SUP_DIS: the commented variant of :1187 (BCE + teacher MSE)
         self.tagger = TagBatch(self.seg_rows, self.C, self.active, self.missing, dataset_idx=dataset_idx,
                                device=self.device)
         self._plan = None
@@ -110,7 +121,8 @@ class ClientShard:
 
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
-                       side_stream=None, after_aggregate=None, aggregate_fn=None, proto_on_side=True) -> RoundResult:
+                       side_stream=None, after_aggregate=None, aggregate_fn=None, counters=None,
+                       aggregate_tails=False) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
@@ -119,16 +131,19 @@ class ClientShard:
         are the shard's persistent buffers (overwritten by the next round).
 
         The pass is a DAG over its inputs: {sim -> select -> mask fill -> loss} needs the incoming
-        global model's features, {prototypes} and {FedAvg} only need the locally trained model.
-        side_stream: run prototypes + FedAvg on this stream, concurrently with the tagging/loss chain
+        global model's features, {prototypes -> aggregation} only the locally trained model.
+        side_stream: run prototypes + aggregation on this stream, concurrently with the tagging/loss chain
         (the latency-bound select / fill / loss kernels hide behind the streaming ones; in the live
-        loop the same split overlaps them with the cuDNN work around them).
-        after_aggregate(glob): called with the FedAvg stream current right after the FedAvg launch —
-        the multi-GPU driver issues its all-reduce there.  The main stream joins before returning.
-        aggregate_fn(client_flats, weights) -> [P] tensor: replaces the FedAvg launch altogether (the
-        fused fold + all-reduce kernel of dist.FusedFedAvgAllReduce).
-        proto_on_side=False keeps the prototype pass on the main stream (multi-GPU: the aggregation
-        with its NVLink-bound phases is then the whole side chain and overlaps HBM-bound work)."""
+        loop the same split overlaps them with the cuDNN work around them).  Without a side stream the
+        stages run back to back as sim, prototypes, aggregation, select, fill, loss: the small kernels
+        follow the aggregation, whose 28 MB of freshly written lines are still being written back.
+        after_aggregate(glob): called with the aggregation stream current right after the FedAvg launch —
+        the NCCL path issues its all-reduce there.
+        aggregate_fn(client_flats, weights, protos) -> [P] tensor (or a tuple (params, proto_glob, tao,
+        counters)): replaces the FedAvg launch altogether (the fused fold + all-reduce kernels of dist.py).
+        aggregate_tails / counters: single-GPU aggregation of the small tails of main.py:218-234 next to
+        FedAvg — FedAvg_proto (bit-exact kernel), FedAvg_tao (float64) and the int64 BatchNorm counters
+        (counters: S int64 tensors of equal length)."""
         N, C, S = self.N, self.C, self.S
         D = feat_tag.shape[1]
         if (tuple(feat_tag.shape) != (N, D) or tuple(feat_proto.shape) != (N, D) or tuple(labels.shape) != (N, C)
@@ -160,7 +175,8 @@ class ClientShard:
                     e.record(stream)
                     ev[name] = e
 
-            out = {"glob": glob}
+            out = {"glob": glob, "proto_glob": None, "tao": None, "counters": None}
+            protos = PrototypeResult(pl.proto, pl.cnt, pl.tcnt, list(self.seg_rows))
 
             def proto_stage(stream_b):
                 sb = stream_b.cuda_stream
@@ -174,7 +190,11 @@ class ClientShard:
             def aggregate_stage(stream_b):
                 sb = stream_b.cuda_stream
                 if aggregate_fn is not None:
-                    out["glob"] = aggregate_fn(client_flats, weights)
+                    r = aggregate_fn(client_flats, weights, protos)
+                    if isinstance(r, tuple):
+                        out["glob"], out["proto_glob"], out["tao"], out["counters"] = r
+                    else:
+                        out["glob"] = r
                 else:
                     flags = cabi.FEDAVG_DIVIDE if divide else 0
                     check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
@@ -182,43 +202,60 @@ class ClientShard:
                                                    sb), "fmlp_fedavg_flat_f32")
                     if after_aggregate is not None:
                         after_aggregate(glob)
+                    if aggregate_tails:
+                        J = int(counters[0].numel()) if counters else 0
+                        if J > 1024:
+                            raise ValueError("at most 1024 int64 counters")
+                        # FedAvg_proto (utils/FedAvg.py:72-93): the bit-exact single-GPU kernel on the clients' prototypes
+                        check(lib.fmlp_proto_avg_f32(pl.proto.data_ptr(), S, C, D, 2, cabi.f64_array(weights), pl.class_active,
+                                                     pl.proto_glob.data_ptr(), sb), "fmlp_proto_avg_f32")
+                        # FedAvg_tao (:51-70, float64) and the int64 counters (:9-13): pack the sums, finalize
+                        check(lib.fmlp_agg_tail_pack_f64(pl.tcnt.data_ptr(), S, C, cabi.f64_array(weights), pl.sizes, pl.active,
+                                                         pl.missing, cabi.ptr_array([c.data_ptr() for c in counters]) if J else None,
+                                                         J, pl.tail.data_ptr(), sb), "fmlp_agg_tail_pack_f64")
+                        check(lib.fmlp_agg_finalize_f32(None, pl.tail.data_ptr(), C, 0, J, float(divisor), None,
+                                                        pl.tao.data_ptr(), pl.counters.data_ptr() if J else None, sb),
+                              "fmlp_agg_finalize_f32")
+                        out["proto_glob"], out["tao"] = pl.proto_glob, pl.tao
+                        out["counters"] = pl.counters[:J] if J else None
                 if stream_b is stream:
                     mark("fedavg")
+
+            def select_fill_loss():
+                check(lib.fmlp_tag_select(tg.sim.data_ptr(), tg.sim.shape[1], tg.tag.data_ptr(), tg.tag.shape[1], C, S,
+                                          pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),
+                                          pl.remaining.data_ptr(), pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(),
+                                          pl.ws_select.numel(), st), "fmlp_tag_select")
+                check(lib.fmlp_mask_fill(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], C, S, pl.rows, pl.active,
+                                         pl.missing, pl.y.data_ptr(), pl.distill.data_ptr(), pl.sup.data_ptr(), st),
+                      "fmlp_mask_fill")
+                mark("select_fill")
+                check(lib.fmlp_loss_stage2_seg_f32(logits.data_ptr(), logits_glob.data_ptr(), pl.y.data_ptr(),
+                                                   pl.distill.data_ptr(), C, S, pl.rows, self.loss_variant,
+                                                   pl.remaining.data_ptr(), pl.losses.data_ptr(), pl.dz.data_ptr(),
+                                                   pl.ws_loss.data_ptr(), pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
+                mark("loss")
 
             mark("start")
             if side_stream is not None:
                 side_stream.wait_stream(stream)
                 with torch.cuda.stream(side_stream):
-                    if proto_on_side:
-                        proto_stage(side_stream)
+                    proto_stage(side_stream)
                     aggregate_stage(side_stream)
             check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
                                        tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], pl.ws_sim.data_ptr(),
                                        pl.ws_sim.numel(), st), "fmlp_tag_sim_f32")
             mark("sim")
-            check(lib.fmlp_tag_select(tg.sim.data_ptr(), tg.sim.shape[1], tg.tag.data_ptr(), tg.tag.shape[1], C, S,
-                                      pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),
-                                      pl.remaining.data_ptr(), pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(),
-                                      pl.ws_select.numel(), st), "fmlp_tag_select")
-            check(lib.fmlp_mask_fill(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], C, S, pl.rows, pl.active,
-                                     pl.missing, pl.y.data_ptr(), pl.distill.data_ptr(), pl.sup.data_ptr(), st),
-                  "fmlp_mask_fill")
-            mark("select_fill")
-            check(lib.fmlp_loss_stage2_seg_f32(logits.data_ptr(), logits_glob.data_ptr(), pl.y.data_ptr(),
-                                               pl.distill.data_ptr(), C, S, pl.rows, cabi.LOSS2_SUP,
-                                               pl.remaining.data_ptr(), pl.losses.data_ptr(), pl.dz.data_ptr(),
-                                               pl.ws_loss.data_ptr(), pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
-            mark("loss")
             if side_stream is not None:
-                if not proto_on_side:
-                    proto_stage(stream)
+                select_fill_loss()
                 stream.wait_stream(side_stream)
             else:
                 proto_stage(stream)
                 aggregate_stage(stream)
+                select_fill_loss()
         if self.keep_history:
             # keep the lazily materialised host lists of the tagger in sync with this round's picks
             tg._history.append((pl.counts.clone(), pl.sel.clone(), pl.cap))
         tg._lists = None
-        return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz,
-                           PrototypeResult(pl.proto, pl.cnt, pl.tcnt, list(self.seg_rows)), out["glob"], ev)
+        return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz, protos, out["glob"], ev,
+                           proto_glob=out["proto_glob"], tao=out["tao"], counters=out["counters"])

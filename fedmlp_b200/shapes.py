@@ -45,6 +45,17 @@ def densenet121_state_shapes(n_classes: int, growth=32, blocks=(6, 12, 24, 16), 
     return out
 
 
+def efficientnet_b0_state_shapes(n_classes: int):
+    """torchvision.models.efficientnet_b0 with `n_classes` outputs: 360 entries, 4,067,498 fp32 values and 49
+    int64 counters at 14 classes (the reference's EfficientNet comes from efficientnet_pytorch, which differs
+    slightly; only the sizes matter to FedAvg).  Shapes are read from torchvision's meta-device model."""
+    import torchvision
+
+    with torch.device("meta"):
+        model = torchvision.models.efficientnet_b0(num_classes=n_classes)
+    return OrderedDict((k, (tuple(v.shape), v.dtype)) for k, v in model.state_dict().items())
+
+
 def synth_state_dict(shapes, seed, device="cpu", base=None, counter=100):
     """Seeded synthetic state_dict of the given layout: N(0, 0.02) around `base`."""
     g = torch.Generator().manual_seed(seed)

@@ -127,6 +127,42 @@ int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* weights, in
                               uint32_t* const* flag_ptrs, int64_t slice_len, int n_chunks, int rank,
                               int world, uint32_t* epoch_dev, fmlp_stream_t stream);
 
+/* Round-2 form of the multi-GPU aggregation: a NON-cooperative work-queue kernel (starts on whatever
+ * SM slots are free, shares the SMs with the tagging kernels of another stream) that reduces through
+ * the NVSwitch (multimem.ld_reduce / multimem.st on a multicast mapping of the symmetric buffers) or,
+ * without multicast, by peer loads in rank order + peer stores.  Replaces main.py:218-234 across ranks:
+ * FedAvg of the flat parameters, plus the small tails riding the same exchange:
+ *   fp32 vector  [ P parameters | T tail floats (sum_k w_k * tail_k, e.g. the 2C*D prototypes) ]
+ *   fp64 tail    [ M scalars ] summed over ranks (class weight sums, n*t sums, int64 counter sums)
+ *   srcs / tail_srcs / weights   host arrays [K]: client buffers (P floats), tail vectors (T floats, or NULL
+ *                    when T == 0) and weights PRE-NORMALISED by the global sum
+ *   tail_f64         device [M] doubles: this rank's partial sums (fmlp_agg_tail_pack_f64), NULL iff M == 0
+ *   partial_ptrs / result_ptrs   host arrays [world]: every rank's symmetric buffers of
+ *                    fmlp_fedavg_allreduce_q_buffer_floats(P, T, M) floats
+ *   flag_ptrs        host array [world]: FMLP_AR_FLAG_WORDS x uint32 per rank, zero-initialised once
+ *   mc_partial / mc_result       multicast addresses of the two buffers, or both NULL (peer-to-peer path)
+ *   max_ctas         0 = one CTA per SM; smaller values leave SMs to concurrent kernels
+ * The result buffer of every rank holds [ mean parameters | tail sums | fp64 sums ] on return
+ * (bit-identical on all ranks).  Collective: every rank launches it with the same shapes.            */
+size_t fmlp_fedavg_allreduce_q_buffer_floats(int64_t P, int64_t T, int M);
+int fmlp_fedavg_allreduce_q_f32(const float* const* srcs, const float* const* tail_srcs, const float* weights,
+                                int K, int64_t P, int64_t T, const double* tail_f64, int M,
+                                float* const* partial_ptrs, float* const* result_ptrs,
+                                uint32_t* const* flag_ptrs, float* mc_partial, float* mc_result, int n_chunks,
+                                int rank, int world, uint32_t* epoch_dev, int max_ctas, fmlp_stream_t stream);
+/* This rank's fp64 partial sums for the exchange above, M = 3C + J (layout in fedavg_allreduce_q.cu):
+ * class weight sums over the annotating clients (FedAvg_proto, utils/FedAvg.py:72-93), n*t sums and weight
+ * sums over the clients that miss the class (FedAvg_tao, :51-70; t = tcnt / rows as at
+ * utils/local_training.py:1000,1249), and the weighted int64 BatchNorm counter sums (FedAvg.py:9-13).
+ *   tcnt device [S][C] int32 (or NULL); weights / rows / act / neg host [S]; counters host [S] device ptrs */
+int fmlp_agg_tail_pack_f64(const int32_t* tcnt, int S, int C, const double* weights, const int64_t* rows,
+                           const uint32_t* act, const uint32_t* neg, const int64_t* const* counters, int J,
+                           double* out, fmlp_stream_t stream);
+/* After the exchange: prototypes = tail sums * (total / class weight) (0 * inf = NaN where nobody annotates
+ * the class, like the reference's 0/0), tao = num / den (1.0 for an empty list), counters as float32.   */
+int fmlp_agg_finalize_f32(const float* proto_sum, const double* tail, int C, int D, int J, double total_weight,
+                          float* proto_out, double* tao_out, float* counters_out, fmlp_stream_t stream);
+
 /* Prototype aggregation, replaces utils/FedAvg.py:72-93 `FedAvg_proto`:
  *   out[2c+j] = (sum over clients i in act(c), in list order, of protos[i][2c+j]*n_i) / sum n_i
  * protos  device [K][2C][D] (stacked client prototypes);  weights host [K] (double);

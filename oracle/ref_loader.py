@@ -1,8 +1,8 @@
-"""Import the reference's own modules from /root/reference (build container only).
+"""Import the reference's own modules: from /root/reference in the build container, else from the
+unmodified copies oracle/vendor_ref.py placed under oracle/_ref/ (git-ignored, travels to the GPU box).
 
-The reference is Python and cannot travel to the GPU box, so this loader is used only by
-oracle/make_golden.py (fixture generation) and tests/test_oracle_vs_reference.py (skipped when
-/root/reference is absent).  Missing plotting / model-zoo dependencies of the reference
+Used by oracle/make_golden.py (fixture generation), tests/test_oracle_vs_reference.py and the CPU arm of
+bench.py (`--impl reference`, `cpu_baseline`).  Missing plotting / model-zoo dependencies of the reference
 (matplotlib, seaborn, tensorboardX, pretrainedmodels, efficientnet_pytorch) are stubbed in
 sys.modules; none of them is touched by the hot path.  TEST INFRASTRUCTURE ONLY.
 """
@@ -13,13 +13,30 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FEDMLP_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("FEDMLP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "utils", "FedAvg.py")):
+        return "/root/reference"
+    return _VENDORED
+
+
+REFERENCE_ROOT = _pick_root()
 _STUBS = ["matplotlib", "matplotlib.pyplot", "seaborn", "tensorboardX", "pretrainedmodels",
           "efficientnet_pytorch"]
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "FedAvg.py"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "local_training.py"))
+
+
+def source() -> str:
+    """Where the reference modules come from: 'mounted' (/root/reference) or 'vendored' (oracle/_ref)."""
+    return "vendored" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_VENDORED) else "mounted"
 
 
 def _install_stubs() -> None:

@@ -33,8 +33,10 @@ def test_round_hot_path_matches_per_client_oracle(lib, mode):
         feat2 = torch.cat([d[0] for d in data2]); logits2 = torch.cat([d[2] for d in data2])
         zg = torch.randn(sum(sizes), C, generator=g) * 2
         proto = O.synth_prototypes(feat, labels)
+        counters = [torch.arange(7, dtype=torch.int64) * (s + 1) + 100 * rnd for s in range(S)]
         res = shard.round_hot_path(feat.to(DEV), proto.to(DEV), logits.to(DEV), zg.to(DEV), labels.to(DEV),
-                                   feat2.to(DEV), logits2.to(DEV), [f.to(DEV) for f in flats], sizes)
+                                   feat2.to(DEV), logits2.to(DEV), [f.to(DEV) for f in flats], sizes,
+                                   aggregate_tails=True, counters=[c.to(DEV) for c in counters])
         t = res.protos.t()
         for s, n in enumerate(sizes):
             r0, r1 = shard.seg_rows[s], shard.seg_rows[s + 1]
@@ -61,3 +63,13 @@ def test_round_hot_path_matches_per_client_oracle(lib, mode):
             np.testing.assert_allclose(t[s], ref_t, rtol=0, atol=1.5 / n)
         ref_glob = O.fedavg([OrderedDict(w=f) for f in flats], sizes)["w"]
         assert torch.equal(res.global_flat.cpu(), ref_glob)
+        # the small tails of the server aggregation (main.py:218-234) on the clients' own outputs
+        class_active = [[s for s in range(S) if c in active[s]] for c in range(C)]
+        class_missing = [[s for s in range(S) if c in shard.missing[s]] for c in range(C)]
+        ref_pg = O.fedavg_proto([res.protos.proto[s].cpu() for s in range(S)], sizes, class_active)
+        got_pg = res.proto_glob.cpu()
+        assert torch.equal(torch.isnan(got_pg), torch.isnan(ref_pg))
+        assert torch.equal(torch.nan_to_num(got_pg), torch.nan_to_num(ref_pg))           # bit-exact kernel (FedAvg.py:72-93)
+        np.testing.assert_allclose(res.tao.cpu().numpy(), O.fedavg_tao([t[s] for s in range(S)], sizes, class_missing), rtol=1e-12)
+        ref_cnt = O.fedavg([OrderedDict(n=c) for c in counters], sizes)["n"]
+        assert torch.equal(res.counters.cpu(), ref_cnt)                                   # int64 sums -> float32 (FedAvg.py:9-13)
