@@ -102,18 +102,30 @@ def fedavg_flat_buffers(bufs, weights, out=None, divisor=None, divide=True):
     return out
 
 
-def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev, div_flag=cabi.FEDAVG_DIVIDE):
+def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev, div_flag=cabi.FEDAVG_DIVIDE, tensors=None):
+    """int64 BatchNorm counters (utils/FedAvg.py:9-13).  Integer weights keep the fold in int64 until the true
+    division; the kernel folds up to 64 clients per launch.  More clients with integer weights: the exact int64
+    partial (the reference's own `w[k] * dict_len[i]` adds, J scalars) is formed first and the kernel only does
+    the int64 -> float32 divide — a float32 `out` cannot carry an int64 partial between launches."""
     lib = cabi.lib()
     K = len(ptrs)
-    if K > cabi.MAX_CLIENTS and integral:
-        raise NotImplementedError("int64 FedAvg with integer weights supports at most 64 clients per call")
     st = cabi.stream_ptr(dev)
+    if K > cabi.MAX_CLIENTS and integral:
+        if tensors is None:
+            raise ValueError("int64 FedAvg over more than 64 clients needs the counter tensors")
+        acc = torch.zeros(J, dtype=torch.int64, device=dev)
+        for t, n in zip(tensors, weights):
+            acc += t.reshape(-1) * int(n)
+        cabi.check(lib.fmlp_fedavg_flat_i64(cabi.ptr_array([acc.data_ptr()]), cabi.f64_array([1.0]), 1, J, float(divisor), 1,
+                                            div_flag, out_ptr, st), "fmlp_fedavg_flat_i64")
+        return acc      # caller keeps it alive until the stream has run
     for g0 in range(0, K, cabi.MAX_CLIENTS):
         g1 = min(K, g0 + cabi.MAX_CLIENTS)
         flags = (cabi.FEDAVG_ACCUMULATE if g0 > 0 else 0) | (div_flag if g1 == K else 0)
         cabi.check(lib.fmlp_fedavg_flat_i64(cabi.ptr_array(ptrs[g0:g1]), cabi.f64_array(weights[g0:g1]), g1 - g0, J,
                                             float(divisor), 1 if integral else 0, flags, out_ptr, st),
                    "fmlp_fedavg_flat_i64")
+    return None
 
 
 def _fedavg_cuda(w, dict_len, divide=True):
@@ -140,15 +152,21 @@ def _fedavg_cuda(w, dict_len, divide=True):
                                                         g1 - g0, layout.n_f32, float(divisor), flags,
                                                         out.flat_f32.data_ptr(), st), "fmlp_fedavg_flat_f32")
             if layout.n_i64:
-                _fedavg_i64_flat([v[1] for v in views], list(dict_len), layout.n_i64, divisor, integral,
-                                 out.flat_f32.data_ptr() + 4 * layout.n_f32, dev, div_flag)
+                ints = None
+                if K > cabi.MAX_CLIENTS and integral:
+                    ints = [sd.flat_i64 if isinstance(sd, FlatStateDict) and sd.flat_i64 is not None else
+                            torch.cat([v.reshape(-1) for i, v in enumerate(sd.values()) if layout.is_int[i]]) for sd in w]
+                out._keepalive = _fedavg_i64_flat([v[1] for v in views], list(dict_len), layout.n_i64, divisor, integral,
+                                                  out.flat_f32.data_ptr() + 4 * layout.n_f32, dev, div_flag, tensors=ints)
             return out
         # ---- multi-tensor path: read the scattered tensors in place ---------------------
-        plan = _multi_plan(layout, dev)
         if K > cabi.MAX_CLIENTS:
-            raise NotImplementedError(
-                "FedAvg over more than 64 scattered state_dicts: wrap the clients with "
-                "FlatStateDict.from_state_dict (flat path has no client limit)")
+            # the pointer table of the multi-tensor kernel holds 64 clients: pack once and take the flat path
+            # (any K, folded in groups of 64 in the reference's client order)
+            packed = [sd if (isinstance(sd, FlatStateDict) and not getattr(sd, "ints_as_float", False))
+                      else FlatStateDict.from_state_dict(sd, device=dev) for sd in w]
+            return _fedavg_cuda(packed, dict_len, divide)
+        plan = _multi_plan(layout, dev)
         f_idx, i_idx = plan["f_idx"], plan["i_idx"]
         Tf, Ti = len(f_idx), len(i_idx)
         vals = [list(sd.values()) for sd in w]
@@ -247,7 +265,7 @@ def FedAvg_proto(Prototypes, weight, class_active_client_list, _rows_per_class=2
     if K == 0:
         raise ValueError("FedAvg_proto of zero clients")
     if K > cabi.MAX_CLIENTS:
-        raise NotImplementedError("FedAvg_proto supports at most 64 clients per call")
+        return _proto_avg_grouped(Prototypes, weight, class_active_client_list, _rows_per_class)
     p0 = Prototypes[0]
     was_cpu = not p0.is_cuda
     if was_cpu and not torch.cuda.is_available():
@@ -277,6 +295,32 @@ def FedAvg_proto(Prototypes, weight, class_active_client_list, _rows_per_class=2
     return out.cpu() if was_cpu else out
 
 
+def _proto_avg_grouped(Prototypes, weight, class_active_client_list, rpc):
+    """More than 64 clients: the kernel's client masks are 64 bits wide, so the clients are averaged in groups
+    of 64 and the group means are combined per class with the groups' class weights by the same kernel.
+    Same value as the reference up to fp32 summation association (<= 1e-6 relative), NaN for an empty class."""
+    K = len(Prototypes)
+    n_listed = len(class_active_client_list)
+    G = cabi.MAX_CLIENTS
+    groups = [range(g0, min(K, g0 + G)) for g0 in range(0, K, G)]
+    means, wsum = [], np.zeros((len(groups), n_listed), dtype=np.float64)
+    for gi, g in enumerate(groups):
+        sub_lists = [[int(c) - g.start for c in clients if g.start <= int(c) < g.stop] for clients in class_active_client_list]
+        for cls, clients in enumerate(class_active_client_list):
+            wsum[gi, cls] = float(sum(weight[int(c)] for c in clients if g.start <= int(c) < g.stop))
+        means.append(FedAvg_proto([Prototypes[i] for i in g], [weight[i] for i in g], sub_lists, rpc))
+    out = torch.zeros_like(means[0])
+    for cls in range(n_listed):
+        members = [gi for gi in range(len(groups)) if wsum[gi, cls] > 0]
+        rows = slice(rpc * cls, rpc * cls + rpc)
+        if not members:
+            out[rows] = float("nan")           # 0/0 in the reference (FedAvg.py:85-86)
+            continue
+        lvl2 = FedAvg_proto([means[gi][rows].contiguous() for gi in range(len(groups))], list(wsum[:, cls]), [members], rpc)
+        out[rows] = lvl2[:rpc]
+    return out
+
+
 def FedAvg_rela(Prototypes, weight, class_active_client_list):
     """utils/FedAvg.py:95-103: like FedAvg_proto with ONE row per class ([C, D] inputs)."""
     return FedAvg_proto(Prototypes, weight, class_active_client_list, _rows_per_class=1)
@@ -298,15 +342,22 @@ def model_dist(w_1, w_2):
         w_2 = OrderedDict((k, v.to(dev)) for k, v in w_2.items())
     cabi.require_cuda(*w_1.values(), *w_2.values())
     layout = layout_of(w_1)
-    if layout_of(w_2) is not layout:
-        raise ValueError("model_dist: the two state_dicts have different shapes / dtypes")
     dev = next(iter(w_1.values())).device
     plan = _multi_plan(layout, dev)
-    f_idx = plan["f_idx"]
+    f_idx = plan["f_idx"]           # the float tensors of w_1: the reference skips on w_1's dtype (FedNoRo.py:110-111)
     T = len(f_idx)
     v1, v2 = list(w_1.values()), list(w_2.values())
-    table = np.array([[v1[t].contiguous().data_ptr() for t in f_idx], [v2[t].contiguous().data_ptr() for t in f_idx]],
-                     dtype=np.int64).reshape(-1)
+    # contiguous float32 operands that OUTLIVE the launch and the .item() sync below (a temporary made by
+    # .contiguous() / .float() could be recycled by the allocator before the kernel runs)
+    a_ops, b_ops = [], []
+    for t in f_idx:
+        a, b = v1[t], v2[t]
+        if a.shape != b.shape:
+            raise ValueError("model_dist: the two state_dicts have different shapes")
+        # w_2 may be a FedAvg output, whose int64 counters became float32: only w_1's float keys matter
+        a_ops.append(a.contiguous() if a.dtype == torch.float32 else a.float().contiguous())
+        b_ops.append(b.contiguous() if b.dtype == torch.float32 else b.float().contiguous())
+    table = np.array([[x.data_ptr() for x in a_ops], [x.data_ptr() for x in b_ops]], dtype=np.int64).reshape(-1)
     lib = cabi.lib()
     with torch.cuda.device(dev):
         table_dev = torch.from_numpy(table).to(dev)
@@ -316,7 +367,9 @@ def model_dist(w_1, w_2):
                                            plan["chunk_tensor"].data_ptr(), plan["chunk_start"].data_ptr(),
                                            plan["tensor_chunk0"].data_ptr(), plan["n_chunks"], T, out.data_ptr(),
                                            ws.data_ptr(), ws.numel(), cabi.stream_ptr(dev)), "fmlp_model_dist_f32")
-        return float(out.item())
+        result = float(out.item())
+    del a_ops, b_ops
+    return result
 
 
 def RSCFed(DMA, w_locals, K, dict_len, M):
@@ -360,7 +413,7 @@ def FedAvg_tao(t, weight, class_active_client_list=None):
     order -> bit-identical); main.py:223 passes the per-class lists of clients that MISS the class."""
     K, n = len(t), len(t[0])
     if K > cabi.MAX_CLIENTS:
-        raise NotImplementedError("FedAvg_tao supports at most 64 clients per call")
+        return _tao_avg_grouped(t, weight, class_active_client_list)
     if not torch.cuda.is_available():
         raise cabi.FedMLPNativeError("FedAvg_tao needs a CUDA device (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -378,3 +431,25 @@ def FedAvg_tao(t, weight, class_active_client_list=None):
         cabi.check(cabi.lib().fmlp_tao_avg_f64(t_dev.data_ptr(), K, n, cabi.f64_array([float(x) for x in weight[:K]]), masks,
                                                float(sum(weight)), out.data_ptr(), cabi.stream_ptr(dev)), "fmlp_tao_avg_f64")
     return out.cpu().numpy()
+
+
+def _tao_avg_grouped(t, weight, class_client_list):
+    """More than 64 clients: per-group results of the kernel combined per class by the same kernel (float64;
+    equal to the reference up to summation association, ~1e-16 relative)."""
+    K, n = len(t), len(t[0])
+    G = cabi.MAX_CLIENTS
+    groups = [range(g0, min(K, g0 + G)) for g0 in range(0, K, G)]
+    lists = class_client_list if class_client_list is not None else [list(range(K))] * n
+    part = np.zeros((len(groups), n), dtype=np.float64)
+    wsum = np.zeros((len(groups), n), dtype=np.float64)
+    for gi, g in enumerate(groups):
+        sub = [[int(c) - g.start for c in clients if g.start <= int(c) < g.stop] for clients in lists]
+        for cls, clients in enumerate(lists):
+            wsum[gi, cls] = float(sum(float(weight[int(c)]) for c in clients if g.start <= int(c) < g.stop))
+        part[gi] = FedAvg_tao([t[i] for i in g], [weight[i] for i in g], sub)
+    out = np.ones(n, dtype=np.float64)
+    for cls in range(n):
+        members = [gi for gi in range(len(groups)) if wsum[gi, cls] > 0]
+        if members:
+            out[cls] = FedAvg_tao([part[gi, cls:cls + 1] for gi in range(len(groups))], list(wsum[:, cls]), [members])[0]
+    return out      # without lists utils/FedAvg.py:56-59 divides by the weight of ALL clients: the grouped mean does too

@@ -103,6 +103,14 @@ class FlatStateDict(OrderedDict):
         torch._foreach_copy_(list(self.values()), [v.detach() for v in state_dict.values()])
         return self
 
+    def __setitem__(self, key, value):
+        """Assigning to an existing key copies INTO the flat view (the dict keeps aliasing its buffers, which is
+        what FedAvg's flat path reads); a new key would break the layout and is refused."""
+        if key in self and isinstance(value, torch.Tensor):
+            OrderedDict.__getitem__(self, key).copy_(value)
+            return
+        raise KeyError(f"FlatStateDict has a fixed layout; cannot add key {key!r}")
+
     def clone(self):
         new = FlatStateDict.empty(self.layout, self.flat_f32.device, getattr(self, "ints_as_float", False))
         new.flat_f32.copy_(self.flat_f32)
@@ -134,10 +142,13 @@ def flat_view_of(state_dict):
                 0 if state_dict.flat_i64 is None else state_dict.flat_i64.data_ptr())
     lay = layout_of(state_dict)
     base_f = base_i = None
+    last_f = None
     for i, v in enumerate(state_dict.values()):
         if not v.is_contiguous():
             return None
         p = v.data_ptr()
+        if not lay.is_int[i]:
+            last_f = v
         if lay.is_int[i]:
             b = p - 8 * lay.offsets[i]
             if base_i is None:
@@ -150,4 +161,12 @@ def flat_view_of(state_dict):
                 base_f = b
             elif b != base_f:
                 return None
+    if base_f is not None:
+        # the flat kernel reads n_f32 floats (padded to 4) with 128-bit loads from the base: the base must be
+        # 16-byte aligned and the last tensor's storage must extend over the padding
+        if base_f % 16:
+            return None
+        st = last_f.untyped_storage()
+        if base_f + 4 * lay.n_f32 > st.data_ptr() + st.nbytes():
+            return None
     return (base_f or 0, base_i or 0)

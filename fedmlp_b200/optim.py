@@ -5,7 +5,9 @@
 layout, and performs `step()` (+ optional `zero_grad`) as ONE kernel launch instead of ~10 foreach
 kernels over 364 tensors.  Same hyper-parameters and arithmetic as the optimizer the reference
 creates every round: torch.optim.Adam(net.parameters(), lr, betas=(0.9, 0.999), weight_decay=5e-4)
-(utils/local_training.py:912-913, :1149-1150).
+(utils/local_training.py:912-913, :1149-1150).  One difference from torch.optim.Adam: a trainable parameter
+that received NO gradient in a step is updated with a zero gradient (decay + moment decay) instead of being
+skipped; frozen parameters (requires_grad=False) are left alone like in torch.
 """
 from __future__ import annotations
 
@@ -32,11 +34,16 @@ class FlatAdam:
         lay = self.flat.layout
         offset_of = {k: (lay.offsets[i], lay.numels[i]) for i, k in enumerate(lay.keys) if not lay.is_int[i]}
         starts, lens = [], []
+        self._bound = []          # (parameter, its gradient view): re-checked in step()
         for name, p in module.named_parameters():
             off, n = offset_of[name]
             if p.data_ptr() != buf.data_ptr() + 4 * off:
                 raise ValueError(f"parameter {name} is not a view of the flat buffer")
-            p.grad = self.grad[off:off + n].view_as(p)       # autograd accumulates in place from now on
+            if not p.requires_grad:
+                continue          # torch.optim.Adam never touches frozen parameters (no decay, no moments)
+            g = self.grad[off:off + n].view_as(p)
+            p.grad = g                                       # autograd accumulates in place from now on
+            self._bound.append((p, g))
             for s in range(0, n, _CHUNK):
                 starts.append(off + s)
                 lens.append(min(_CHUNK, n - s))
@@ -45,11 +52,23 @@ class FlatAdam:
         self.chunk_len = torch.tensor(lens, dtype=torch.int32, device=dev)
         self.n_chunks = len(starts)
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=False):
+        """Clears the flat gradient buffer.  (module.zero_grad() / set_to_none=True would detach the parameters'
+        .grad views; step() re-binds them if that happened.)"""
         self.grad.zero_()
+        self._rebind()
+
+    def _rebind(self):
+        for p, g in self._bound:
+            if p.grad is None:
+                p.grad = g                                   # detached by a zero_grad(set_to_none=True): nothing was accumulated
+            elif p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)                              # autograd allocated a fresh .grad: take its values, alias again
+                p.grad = g
 
     def step(self, zero_grad=False):
         """One Adam step; zero_grad=True also clears the gradients in the same launch."""
+        self._rebind()
         self.step_count += 1
         buf = self.flat.flat_f32
         with torch.cuda.device(buf.device):
