@@ -52,6 +52,15 @@ class FlatAdam:
         self.chunk_len = torch.tensor(lens, dtype=torch.int32, device=dev)
         self.n_chunks = len(starts)
 
+    def reset(self, lr=None):
+        """Fresh optimizer state (the reference re-creates Adam every round, :912, :1149): zero the moments and
+        the step count, keep the buffers."""
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.grad.zero_()
+        self.step_count = 0
+        if lr is not None:
+            self.lr = float(lr)
+        self._rebind()
+
     def zero_grad(self, set_to_none=False):
         """Clears the flat gradient buffer.  (module.zero_grad() / set_to_none=True would detach the parameters'
         .grad views; step() re-binds them if that happened.)"""

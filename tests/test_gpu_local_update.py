@@ -183,3 +183,150 @@ def test_flat_adam_matches_torch_adam(lib):
     import fedmlp_b200 as F
     out = F.FedAvg([opt.flat, opt.flat.clone()], [3, 5])
     np.testing.assert_allclose(out["fc1.weight"].cpu().numpy(), net.state_dict()["fc1.weight"].cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Whole-call equivalence with the RECORDED reference run (tests/golden/flow.npz = the unmodified
+# LocalUpdate.train_FedMLP driven on CPU by oracle/make_golden.py): same dataset, model, seeds, call sequence.
+def test_local_update_whole_call_matches_recorded_reference_run(lib):
+    import copy
+    import random
+
+    import golden_util as gu
+    import oracle.make_golden as G
+    from fedmlp_b200.local_training import LocalUpdate
+
+    z = gu.load("flow.npz")
+    N, C, FEAT, CLIENT = int(z["meta/N"]), int(z["meta/C"]), int(z["meta/FEAT"]), int(z["meta/client"])
+    DIM = 12
+
+    class GpuTinyNet(G.TinyNet):
+        """The golden run's model on the GPU.  __deepcopy__ draws from the global RNG exactly like the
+        reference run's (a fresh TinyNet is initialised, then overwritten), so the loaders shuffle alike."""
+
+        def __deepcopy__(self, memo):
+            new = GpuTinyNet(self.fc1.in_features, self.fc1.out_features, self.fc2.out_features)
+            new.load_state_dict(copy.deepcopy(self.state_dict()))
+            new.role = "global"
+            new.train(self.training)
+            return new.to(self.fc1.weight.device)
+
+    # ---- the exact preamble of oracle/make_golden.py:make_flow
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    ds = G.SynthDataset(N, C, DIM, seed=99)
+    assert np.array_equal(ds.targets, z["meta/targets_true"])
+    idxs = [int(v) for v in z["meta/idxs"]]
+    rows, cols = np.where(ds.targets == 1)
+    class_neg_idx = [rows[np.where(cols == i)[0]] for i in range(C)]
+    args = G.make_flow_args(device="cuda")
+    net = GpuTinyNet(DIM, FEAT, C)                       # initialised on the CPU from the global RNG, like the golden run
+    G.TRACE.clear()
+    local = LocalUpdate(args, CLIENT, copy.deepcopy(ds), idxs, class_neg_idx, class_neg_idx, active_class_list=[CLIENT])
+    tao = [0] * C
+    neg_in = [c for c in range(C) if c != CLIENT]
+
+    def step_losses(prefix):
+        kinds = [str(k) for k in z[f"{prefix}/kinds"]]
+        return [float(z[f"{prefix}/{i}/loss"]) for i, k in enumerate(kinds) if k == "loss"]
+
+    # ---- last stage-1 round
+    rnd = args.rounds_FedMLP_stage1 - 1
+    work = copy.deepcopy(net).cuda()
+    ret = local.train_FedMLP(rnd, tao, [], None, neg_in, [CLIENT], work)
+    got = [float(s["loss"]) for s in local.last["steps"]]
+    ref = step_losses("s1")
+    assert len(got) == len(ref)
+    np.testing.assert_allclose(got, ref, rtol=2e-4)               # same batches in the same order, CPU vs GPU fp32
+    assert abs(ret[1] - float(z["s1/loss_mean"])) <= 2e-4 * abs(float(z["s1/loss_mean"]))
+    assert ret[4] == [int(v) for v in z["s1/neg_list"]] and ret[5] == [int(v) for v in z["s1/act_list"]]
+    np.testing.assert_allclose(ret[6], z["s1/t"], rtol=0, atol=1.5 / len(idxs))
+    np.testing.assert_allclose(ret[7].numpy(), z["s1/proto"], rtol=2e-3, atol=2e-4)
+    proto_glob = torch.from_numpy(z["proto_glob"].copy())
+    # ---- two stage-2 rounds: tagging state, losses, prototypes, t
+    for r in range(2):
+        rnd = args.rounds_FedMLP_stage1 + r
+        work2 = copy.deepcopy(work)
+        ret = local.train_FedMLP(rnd, tao, proto_glob, None, list(neg_in), [CLIENT], work2)
+        for j in range(2 * len(neg_in)):
+            assert local.traindata_idx[j] == [float(v) for v in z[f"s2_{r}/traindata_idx/{j}"]], (r, j)
+        for j in range(len(neg_in)):
+            assert sorted(local.idxss[j]) == [int(v) for v in z[f"s2_{r}/idxss/{j}"]]
+        got = [float(s["loss"]) for s in local.last["steps"]]
+        np.testing.assert_allclose(got, step_losses(f"s2_{r}"), rtol=5e-4)
+        assert abs(ret[1] - float(z[f"s2_{r}/loss_mean"])) <= 5e-4 * abs(float(z[f"s2_{r}/loss_mean"]))
+        np.testing.assert_allclose(ret[6], z[f"s2_{r}/t"], rtol=0, atol=1.5 / len(idxs))
+        np.testing.assert_allclose(ret[7].numpy(), z[f"s2_{r}/proto"], rtol=5e-3, atol=5e-4)
+        work = work2
+    G.TRACE.clear()
+
+
+def test_round_loop_flat_parameters_match_the_reference_copies(lib):
+    """run_fedmlp_rounds(flat=True) — one model per client living in a flat buffer, FlatAdam, FedAvg on the flat
+    buffers, one flat copy per load — against flat=False (deepcopy / torch.optim.Adam / load_state_dict, the
+    reference's plumbing) from identical seeds."""
+    from fedmlp_b200.local_training import LocalUpdate, run_fedmlp_rounds
+    outs = []
+    for flat in (False, True):
+        args = _args()
+        ds, class_neg_idx, dict_users, netglob = _setup()
+        torch.manual_seed(11)
+        trainers = [LocalUpdate(args, i, deepcopy(ds), dict_users[i], class_neg_idx, class_neg_idx, active_class_list=[i])
+                    for i in range(3)]
+        dict_len = [len(dict_users[i]) for i in range(3)]
+        tao, Prototype, hist = run_fedmlp_rounds(args, netglob, trainers, dict_len, rounds=4, flat=flat)
+        outs.append(dict(sd={k: v.detach().cpu().clone() for k, v in netglob.state_dict().items()}, tao=tao,
+                         proto=Prototype.cpu(), hist=hist, idx=[tr.traindata_idx for tr in trainers]))
+    a, b = outs
+    assert b["sd"]["bn.num_batches_tracked"].dtype == torch.int64
+    assert torch.equal(a["sd"]["bn.num_batches_tracked"], b["sd"]["bn.num_batches_tracked"])
+    for k in a["sd"]:
+        if a["sd"][k].is_floating_point():
+            np.testing.assert_allclose(b["sd"][k].numpy(), a["sd"][k].numpy(), rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(b["hist"], a["hist"], rtol=1e-3)
+    np.testing.assert_allclose(b["tao"], a["tao"], atol=2.0 / 104)
+    m = ~torch.isnan(a["proto"])
+    assert torch.equal(torch.isnan(a["proto"]), torch.isnan(b["proto"]))
+    np.testing.assert_allclose(b["proto"][m].numpy(), a["proto"][m].numpy(), rtol=5e-3, atol=5e-4)
+
+
+class _ConvBackbone(nn.Module):
+    def __init__(self, dim, feat_dim):
+        super().__init__()
+        self.conv = nn.Conv2d(dim, feat_dim, 1)
+
+    def forward(self, x):                       # x [B, dim] -> a [B, dim, 3, 3] "image"
+        img = x[:, :, None, None] * torch.linspace(0.5, 1.5, 9, device=x.device).view(1, 1, 3, 3)
+        return self.conv(img)
+
+
+def test_local_update_fused_tail_tagging_matches_the_materialised_path(lib):
+    """SURVEY 8f.1 in the drop-in: a FusedTail model tags through the pool+score kernel (no [N, D] matrix);
+    same selections / masks as the same model run through the materialised feature path."""
+    import fedmlp_b200 as F
+    from fedmlp_b200.local_training import LocalUpdate
+
+    class Plain(nn.Module):                     # same arithmetic, but without .tagging -> materialised path
+        def __init__(self, fused):
+            super().__init__()
+            self.fused = fused
+
+        def forward(self, x):
+            return self.fused(x)
+
+    args = _args()
+    ds, class_neg_idx, dict_users, _ = _setup()
+    torch.manual_seed(21)
+    fused = F.FusedTail(_ConvBackbone(12, 64), nn.Linear(64, 5)).cuda()
+    k, act, neg = 1, [1], [0, 2, 3, 4]
+    proto_glob = torch.relu(torch.randn(10, 64, generator=torch.Generator().manual_seed(1))) + 0.05
+    res = []
+    for model in (fused, Plain(fused)):
+        torch.manual_seed(5)
+        local = LocalUpdate(args, k, deepcopy(ds), dict_users[k], class_neg_idx, class_neg_idx, active_class_list=[k])
+        local.lr = 0.0                               # keep the model fixed: both passes see the same weights
+        net = deepcopy(model)
+        ret = local.train_FedMLP(2, [0] * 5, proto_glob, None, neg, act, net)
+        res.append(dict(idx=local.traindata_idx, idxss=local.idxss, feat=local.last["tag_feat"], sim=local.tagger.sim.cpu().clone()))
+    assert res[0]["feat"] is None and res[1]["feat"] is not None          # the fused pass never built [N, D]
+    np.testing.assert_allclose(res[0]["sim"][neg].numpy(), res[1]["sim"][neg].numpy(), rtol=0, atol=1e-6)
+    assert res[0]["idx"] == res[1]["idx"] and res[0]["idxss"] == res[1]["idxss"]
