@@ -354,7 +354,7 @@ static int launch_sim(SimArgs& a, const SimFeat& ft, cudaStream_t st) {
         if (const char* e = getenv("FMLP_SIM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 16) max_stages = v; }
     }
     int S = max_stages;
-    auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + (size_t)Cfg::W * s * sizeof(uint64_t); };
+    auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + ((size_t)Cfg::W * s + 2) * sizeof(uint64_t); };   // ring barriers + the table barrier
     while (S > 2 && smem_of(S) > budget) --S;
     const size_t smem = smem_of(S);
     if (smem > budget) return FMLP_ERR_UNSUPPORTED;
