@@ -15,13 +15,14 @@ from .fedavg import (DaAgg, FedAvg, FedAvg_proto, FedAvg_rela, FedAvg_tao, Fed_w
 from .flat import FlatLayout, FlatStateDict, flatten_module_, layout_of
 from .losses import (fedmlp_stage1_loss, fedmlp_stage2_loss, fused_loss_and_grad_stage1,
                      fused_loss_and_grad_stage2)
+from .optim import FlatAdam
 from .pooling import FusedTail, SimTable, build_sim_table, pool_tag
 from .prototypes import PrototypeResult, build_prototypes
 from .tagging import TagBatch, tag_similarity
 
 __all__ = [
     "FedAvg", "Fed_w", "FedAvg_proto", "FedAvg_tao", "FedAvg_rela", "RSCFed", "DaAgg", "model_dist", "fedavg_flat_buffers",
-    "FlatLayout", "FlatStateDict", "flatten_module_", "layout_of",
+    "FlatLayout", "FlatStateDict", "flatten_module_", "layout_of", "FlatAdam",
     "fedmlp_stage1_loss", "fedmlp_stage2_loss", "fused_loss_and_grad_stage1", "fused_loss_and_grad_stage2",
     "PrototypeResult", "build_prototypes", "TagBatch", "tag_similarity",
     "FusedTail", "SimTable", "build_sim_table", "pool_tag",

@@ -72,7 +72,9 @@ struct SimArgs {
 template <int NPAIR, bool FOLD>
 struct SimCfg {
     static constexpr int NV = FOLD ? NPAIR : 2 * NPAIR;
-    static constexpr int W = FMLP_SIM_W;                                  // compute warps per CTA
+    // compute warps per CTA; wide pair-mode launches (NV > 16) halve it: their class-vector table and
+    // partial-sum staging would not leave room for the rings otherwise
+    static constexpr int W = (NV > 16 && FMLP_SIM_W > 4) ? 4 : FMLP_SIM_W;
     static constexpr int RT = (NV <= 8) ? FMLP_SIM_RT_SMALL : FMLP_SIM_RT_LARGE;  // rows per thread
     static constexpr int ROWS = 32 * RT;                                  // rows per tile
     static constexpr int THREADS = 32 * W;
@@ -165,7 +167,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
     constexpr int NV = Cfg::NV, RT = Cfg::RT, W = Cfg::W, ROWS = Cfg::ROWS, PV = Cfg::PV;
     constexpr int STAGE = Cfg::STAGE_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int S = a.S, D = a.D, NG = a.NG;
+    const int S = a.S, NG = a.NG;
     // [W][S] boxes (1024-byte aligned: the swizzle pattern is a function of the address bits)
     unsigned char* sRing = smem_raw;
     float* sP = reinterpret_cast<float*>(sRing + (size_t)W * S * STAGE);   // [NG*8 column quads][NV] float4
@@ -338,6 +340,16 @@ static bool sim_use_pdl() {
 
 static size_t sim_table_floats(int nv, int npair, int NG) { return (size_t)NG * 32 * nv + ((2 * npair + 3) & ~3); }
 
+// Shared memory of a launch that scores `npair` classes with two ring stages (mirrors SimCfg / launch_sim).
+static size_t sim_smem_min(int npair, bool fold, int NG) {
+    const int nv = fold ? npair : 2 * npair;
+    const int W = (nv > 16 && FMLP_SIM_W > 4) ? 4 : FMLP_SIM_W;
+    const int RT = (nv <= 8) ? FMLP_SIM_RT_SMALL : FMLP_SIM_RT_LARGE;
+    const size_t rows = 32 * RT;
+    const size_t fixed = ((size_t)NG * 32 * nv + (size_t)W * (nv + 1) * rows + ((2 * npair + 3) & ~3)) * sizeof(float);
+    return (size_t)W * 2 * rows * 128 + fixed + ((size_t)W * 2 + 2) * sizeof(uint64_t);
+}
+
 struct SimFeat {
     const float* feat;
     int64_t ld_feat;
@@ -449,13 +461,19 @@ extern "C" int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const
     a.D = D; a.NG = (D + 31) >> 5; a.C = C; a.S = 0;
     const SimFeat ft = {feat, ld_feat};
     cudaStream_t st = (cudaStream_t)stream;
-    // More than 16 classes in one launch: split the class set (features are re-read per group).
-    if (npair > 16) {
+    // Classes per launch: at most 16, and few enough for the class-vector table + partial staging + two ring
+    // stages to fit in shared memory (wide D in pair mode).  A larger class set is split across launches;
+    // the features are then re-read per group.
+    const bool fold = mode == FMLP_SIM_FOLDED;
+    int group = npair < 16 ? npair : 16;
+    while (group > 1 && sim_smem_min(group, fold, a.NG) > 227u * 1024u) --group;
+    if (sim_smem_min(group, fold, a.NG) > 227u * 1024u) return FMLP_ERR_UNSUPPORTED;
+    if (npair > group) {
         SimArgs b = a;
-        for (int base = 0; base < npair; base += 16) {
-            const int n = (npair - base) < 16 ? (npair - base) : 16;
-            for (int q = 0; q < 16; ++q) b.cls[q] = q < n ? a.cls[base + q] : 0;
-            rc = (mode == FMLP_SIM_FOLDED) ? dispatch_sim<true>(n, b, ft, st) : dispatch_sim<false>(n, b, ft, st);
+        for (int base = 0; base < npair; base += group) {
+            const int n = (npair - base) < group ? (npair - base) : group;
+            for (int q = 0; q < FMLP_MAX_CLASSES; ++q) b.cls[q] = q < n ? a.cls[base + q] : 0;
+            rc = fold ? dispatch_sim<true>(n, b, ft, st) : dispatch_sim<false>(n, b, ft, st);
             if (rc != FMLP_OK) return rc;
         }
         return FMLP_OK;

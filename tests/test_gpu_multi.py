@@ -107,7 +107,8 @@ def _agg_worker(rank, world, port, K, P, C, D, J, n_chunks, multicast, ret):
                                           [rows[i] for i in mine], [active[i] for i in mine], [missing[i] for i in mine],
                                           float(sum(weights)), [counters[i].cuda() for i in mine])
             torch.cuda.synchronize()
-            outs.append(dict(params=params.cpu().clone(), proto=proto.cpu().clone(), tao=tao.cpu().clone(), cnt=cnt.cpu().clone()))
+            outs.append(dict(params=params.cpu().clone(), proto=proto.cpu().clone(), tao=tao.cpu().clone(),
+                             cnt=None if cnt is None else cnt.cpu().clone()))
         ret[rank] = dict(outs=outs, path=agg.exchange.path)
     finally:
         dist.destroy_process_group()

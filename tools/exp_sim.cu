@@ -108,10 +108,30 @@ int main(int argc, char** argv) {
         CK(cudaDeviceSynchronize());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         const double us = ms * 1e3 / iters;
+        // the same call captured in a CUDA graph (does the programmatic dependent launch survive capture?)
+        double us_graph = -1.0;
+        {
+            cudaStream_t cs; CK(cudaStreamCreate(&cs));
+            cudaGraph_t g; cudaGraphExec_t ge;
+            if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                fmlp_tag_sim_f32(feat, D, D, proto, C, S, rows.data(), missing.data(), sim, N, mode, ws, ws_bytes, cs);
+                if (cudaStreamEndCapture(cs, &g) == cudaSuccess && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+                    for (int i = 0; i < 5; ++i) cudaGraphLaunch(ge, cs);
+                    CK(cudaStreamSynchronize(cs));
+                    CK(cudaEventRecord(e0, cs));
+                    for (int i = 0; i < iters; ++i) cudaGraphLaunch(ge, cs);
+                    CK(cudaEventRecord(e1, cs));
+                    CK(cudaStreamSynchronize(cs));
+                    float msg; CK(cudaEventElapsedTime(&msg, e0, e1));
+                    us_graph = msg * 1e3 / iters;
+                }
+            }
+            cudaGetLastError();
+        }
         const double bytes = 4.0 * N * D + 8.0 * C * D + 4.0 * (C - 1) * N;
-        printf("{\"variant\": \"%s\", \"N\": %lld, \"D\": %d, \"C\": %d, \"S\": %d, \"mode\": \"%s\", \"us\": %.2f, \"gbs\": %.1f, "
+        printf("{\"variant\": \"%s\", \"N\": %lld, \"D\": %d, \"C\": %d, \"S\": %d, \"mode\": \"%s\", \"us\": %.2f, \"us_graph\": %.2f, \"gbs\": %.1f, "
                "\"frac_6448\": %.3f, \"max_abs_err\": %.3g, \"bad\": %lld, \"checked\": %lld, \"stages_env\": \"%s\"}\n",
-               EXP_VARIANT, (long long)N, D, C, S, mode ? "folded" : "pair", us, bytes / us / 1e3, bytes / us / 1e3 / 6447.8,
+               EXP_VARIANT, (long long)N, D, C, S, mode ? "folded" : "pair", us, us_graph, bytes / us / 1e3, bytes / us / 1e3 / 6447.8,
                maxerr, bad, written, getenv("FMLP_SIM_STAGES") ? getenv("FMLP_SIM_STAGES") : "");
         fflush(stdout);
     }
