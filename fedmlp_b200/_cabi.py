@@ -44,7 +44,7 @@ SIGNATURES = {
     "fmlp_fedavg_multi_i64": (_i, [_p, _p, _p, _p, _i64, _i, _p, _i, _d, _i, _i, _p]),
     "fmlp_fedavg_allreduce_f32": (_i, [_p, _p, _i, _i64, _p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "fmlp_fedavg_allreduce_q_buffer_floats": (_sz, [_i64, _i64, _i]),
-    "fmlp_fedavg_allreduce_q_f32": (_i, [_p, _p, _p, _i, _i64, _i64, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p]),
+    "fmlp_fedavg_allreduce_q_f32": (_i, [_p, _p, _p, _i, _i64, _i64, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _p]),
     "fmlp_agg_tail_pack_f64": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fmlp_agg_finalize_f32": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _p, _p]),
     "fmlp_proto_avg_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),

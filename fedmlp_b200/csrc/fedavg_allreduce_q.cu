@@ -404,7 +404,7 @@ extern "C" int fmlp_fedavg_allreduce_q_f32(const float* const* srcs, const float
                                            float* const* partial_ptrs, float* const* result_ptrs,
                                            uint32_t* const* flag_ptrs, float* mc_partial, float* mc_result,
                                            int n_chunks, int rank, int world, uint32_t* epoch_dev, int max_ctas,
-                                           fmlp_stream_t stream) {
+                                           int fold_iters_arg, int red_iters_arg, fmlp_stream_t stream) {
     if (!srcs || !weights || !partial_ptrs || !result_ptrs || !flag_ptrs || !epoch_dev || K < 1 || K > FMLP_MAX_CLIENTS ||
         P < 0 || T < 0 || M < 0 || M > kQThreads || world < 1 || world > kQMaxRanks || rank < 0 || rank >= world ||
         n_chunks < 1 || n_chunks > kQMaxChunks)
@@ -440,18 +440,24 @@ extern "C" int fmlp_fedavg_allreduce_q_f32(const float* const* srcs, const float
     const int64_t per_slice = (a.V + (int64_t)n_chunks * world - 1) / ((int64_t)n_chunks * world);
     a.Vs = per_slice < 1 ? 1 : per_slice;
     a.Vc = a.Vs * world;
-    a.FJ = blocks;                                   // one fold piece per CTA and chunk
-    a.Vf = (a.Vc + a.FJ - 1) / a.FJ;
-    a.Vf = (a.Vf + 31) & ~(int64_t)31;               // whole warps of float4
+    // Pieces are whole multiples of the CTA's thread count (a ragged last iteration would idle 31 of 32 warps).
+    //   fold pieces: fold_iters float4 per thread (x K loads each): fine-grained, the scheduler warp prefetches
+    //   reduce pieces: red_iters float4 per thread: the NVLink round trip is ~3 us, so the phase is latency-bound
+    //   and wants EVERY element of the slice in flight at once -> as many pieces (CTAs) as the slice has work for
+    static int fold_iters = 0, red_iters = 0;
+    if (fold_iters == 0) {
+        fold_iters = 2; red_iters = 2;
+        if (const char* e = getenv("FMLP_ARQ_FOLD_ITERS")) { int v = atoi(e); if (v >= 1 && v <= 64) fold_iters = v; }
+        if (const char* e = getenv("FMLP_ARQ_RED_ITERS")) { int v = atoi(e); if (v >= 1 && v <= 64) red_iters = v; }
+    }
+    const int fi = (fold_iters_arg >= 1 && fold_iters_arg <= 64) ? fold_iters_arg : fold_iters;
+    const int ri = (red_iters_arg >= 1 && red_iters_arg <= 64) ? red_iters_arg : red_iters;
+    a.Vf = (int64_t)kQThreads * fi;
     a.FJ = (int)((a.Vc + a.Vf - 1) / a.Vf);
-    // reduce pieces: enough CTAs to keep the links busy, each piece >= 4 float4 per thread
-    int rj = 16;
-    if (const char* e = getenv("FMLP_ARQ_RJ")) { int v = atoi(e); if (v >= 1 && v <= 256) rj = v; }
-    while (rj > 1 && a.Vs / rj < (int64_t)kQThreads * 2) rj >>= 1;
-    a.RJ = rj;
-    a.Vr = (a.Vs + a.RJ - 1) / a.RJ;
-    a.Vr = (a.Vr + 31) & ~(int64_t)31;
+    a.Vr = (int64_t)kQThreads * ri;
     a.RJ = (int)((a.Vs + a.Vr - 1) / a.Vr);
+    if (a.FJ < 1) a.FJ = 1;
+    if (a.RJ < 1) a.RJ = 1;
     if (mc_partial)
         fedavg_allreduce_q_kernel<true><<<blocks, kQThreads + 32, 0, (cudaStream_t)stream>>>(a);
     else

@@ -154,7 +154,7 @@ class QueuedAggregation:
     FLAG_WORDS = 512      # FMLP_AR_FLAG_WORDS
 
     def __init__(self, P: int, T: int = 0, M: int = 0, group=None, device=None, n_chunks=None, max_ctas=None,
-                 use_multicast=None):
+                 use_multicast=None, fold_iters=0, red_iters=0):
         import os
 
         import torch.distributed._symmetric_memory as symm
@@ -174,6 +174,7 @@ class QueuedAggregation:
             n_chunks = int(os.environ.get("FMLP_ARQ_CHUNKS", "4"))
         self.n_chunks = max(1, min(16, int(n_chunks)))
         self.max_ctas = int(os.environ.get("FMLP_ARQ_CTAS", "0")) if max_ctas is None else int(max_ctas)
+        self.fold_iters, self.red_iters = int(fold_iters), int(red_iters)
         self.partial = symm.empty(n, dtype=torch.float32, device=self.device)
         self.result = symm.empty(n, dtype=torch.float32, device=self.device)
         self.flags = symm.empty(self.FLAG_WORDS, dtype=torch.int32, device=self.device)
@@ -243,8 +244,8 @@ class QueuedAggregation:
                 cabi.ptr_array([b.data_ptr() for b in local_bufs]), tails, cabi.f32_array(weights_normalised), K,
                 self.P, self.T, tail_f64.data_ptr() if self.M else None, self.M,
                 self.partial_ptrs, self.result_ptrs, self.flag_ptrs, self.mc_partial or None, self.mc_result or None,
-                self.n_chunks, self.rank, self.world, self.epoch_dev.data_ptr(), self.max_ctas,
-                cabi.stream_ptr(self.device)), "fmlp_fedavg_allreduce_q_f32")
+                self.n_chunks, self.rank, self.world, self.epoch_dev.data_ptr(), self.max_ctas, self.fold_iters,
+                self.red_iters, cabi.stream_ptr(self.device)), "fmlp_fedavg_allreduce_q_f32")
         r = self.result
         f64 = r[self.P + self.T:self.P + self.T + 2 * self.M].view(torch.float64) if self.M else None
         return r[:self.P], (r[self.P:self.P + self.T] if self.T else None), f64

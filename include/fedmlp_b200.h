@@ -142,6 +142,8 @@ int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* weights, in
  *   flag_ptrs        host array [world]: FMLP_AR_FLAG_WORDS x uint32 per rank, zero-initialised once
  *   mc_partial / mc_result       multicast addresses of the two buffers, or both NULL (peer-to-peer path)
  *   max_ctas         0 = one CTA per SM; smaller values leave SMs to concurrent kernels
+ *   fold_iters / red_iters   float4 per thread of a fold / reduce work item (0 = defaults); the same values
+ *                    must be used for every call on one set of flag words
  * The result buffer of every rank holds [ mean parameters | tail sums | fp64 sums ] on return
  * (bit-identical on all ranks).  Collective: every rank launches it with the same shapes.            */
 size_t fmlp_fedavg_allreduce_q_buffer_floats(int64_t P, int64_t T, int M);
@@ -149,7 +151,8 @@ int fmlp_fedavg_allreduce_q_f32(const float* const* srcs, const float* const* ta
                                 int K, int64_t P, int64_t T, const double* tail_f64, int M,
                                 float* const* partial_ptrs, float* const* result_ptrs,
                                 uint32_t* const* flag_ptrs, float* mc_partial, float* mc_result, int n_chunks,
-                                int rank, int world, uint32_t* epoch_dev, int max_ctas, fmlp_stream_t stream);
+                                int rank, int world, uint32_t* epoch_dev, int max_ctas, int fold_iters,
+                                int red_iters, fmlp_stream_t stream);
 /* This rank's fp64 partial sums for the exchange above, M = 3C + J (layout in fedavg_allreduce_q.cu):
  * class weight sums over the annotating clients (FedAvg_proto, utils/FedAvg.py:72-93), n*t sums and weight
  * sums over the clients that miss the class (FedAvg_tao, :51-70; t = tcnt / rows as at
