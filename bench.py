@@ -70,9 +70,13 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--collective", default="queue", choices=["queue", "fused_r01", "nccl"],
-                    help="N>1: work-queue fold + NVLS/P2P all-reduce kernel with the packed tails (default), the round-1 "
-                         "cooperative peer-store kernel, or local fold + NCCL all-reduce")
+    ap.add_argument("--collective", default="queue_split", choices=["queue_split", "queue", "fused_r01", "nccl"],
+                    help="N>1: queue_split = work-queue fold + NVLS/P2P all-reduce kernel for the parameters on its own stream "
+                         "from the start of the round + a second single-chunk launch for the packed tails after the prototype pass "
+                         "(default); queue = one exchange for parameters + tails; fused_r01 = the round-1 cooperative peer-store "
+                         "kernel (parameters only); nccl = local fold + NCCL all-reduce (parameters only)")
+    ap.add_argument("--streams", type=int, default=3, choices=[2, 3],
+                    help="3: tagging/loss chain || prototypes + tails || parameter aggregation; 2: the last two share a stream")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     return ap.parse_args()
 
@@ -363,6 +367,7 @@ class Runner:
         self.shard.loss_variant = cabi.LOSS2_SUP_DIS if w.loss == "sup_dis" else cabi.LOSS2_SUP
         self.fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
         self.side_stream = torch.cuda.Stream(device=dev)
+        self.agg_stream = torch.cuda.Stream(device=dev) if a.streams == 3 else None
         self.total_w = float(sum(inp["weights"]) * world)
         self.w_norm = [x / self.total_w for x in inp["weights"]]          # pre-normalised: the all-reduce yields the mean
         self.agg = self.fused = None
@@ -370,12 +375,15 @@ class Runner:
         if world > 1:
             self.collective = "nccl all_reduce after the local fold (parameters only)"
             try:
-                if a.collective == "queue":
+                if a.collective in ("queue", "queue_split"):
                     from fedmlp_b200.dist import FedMLPAggregation
-                    self.agg = FedMLPAggregation(inp["Ppad"], C, w.D, inp["J"], device=dev)
+                    self.agg = FedMLPAggregation(inp["Ppad"], C, w.D, inp["J"], device=dev, split=(a.collective == "queue_split"))
                     ex = self.agg.exchange
-                    self.collective = (f"work-queue fold + all-reduce kernel ({ex.path}), {ex.n_chunks} chunks, parameters + prototype "
-                                       f"sums + fp64 tail (class weights, tao, {inp['J']} int64 counters) in one exchange")
+                    self.collective = (f"work-queue fold + all-reduce kernel ({ex.path}), {ex.n_chunks} chunks: " +
+                                       ("parameters in their own exchange from the start of the round; prototype sums + fp64 tail (class "
+                                        f"weights, tao, {inp['J']} int64 counters) in a second single-chunk launch after the prototype pass"
+                                        if self.agg.split else
+                                        f"parameters + prototype sums + fp64 tail (class weights, tao, {inp['J']} int64 counters) in one exchange"))
                 elif a.collective == "fused_r01":
                     from fedmlp_b200.dist import FusedFedAvgAllReduce
                     self.fused = FusedFedAvgAllReduce(inp["Ppad"], device=dev)
@@ -391,13 +399,23 @@ class Runner:
         {sim -> select -> fill -> loss}; the per-stage event timing (timers) runs the stages back to back on one
         stream so every kernel is timed alone."""
         side = self.side_stream if (overlap and timers is None) else None
+        aggs = self.agg_stream if side is not None else None
         inp = data if data is not None else self.inp
         sh, w = self.shard, self.w
         args = (inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"], inp["feat_proto"],
                 inp["logits_proto"], inp["flats"])
         if self.world == 1:
             return sh.round_hot_path(*args, inp["weights"], timers=timers, fedavg_out=self.fed_out, side_stream=side,
-                                     aggregate_tails=True, counters=inp["counters"])
+                                     agg_stream=aggs, aggregate_tails=True, counters=inp["counters"])
+        if self.agg is not None and self.agg.split:
+            def params_fn(bufs, wts):
+                return self.agg.aggregate_params(bufs, inp["weights"], self.total_w)
+
+            def tails_fn(protos):
+                return self.agg.aggregate_tails([protos.proto[k] for k in range(w.S)], protos.tcnt, inp["weights"], [w.n] * w.S,
+                                                sh.active, sh.missing, self.total_w, inp["counters"])
+            return sh.round_hot_path(*args, self.w_norm, timers=timers, fedavg_out=self.fed_out, divide=False,
+                                     side_stream=side, agg_stream=aggs, params_fn=params_fn, tails_fn=tails_fn)
         if self.agg is not None:
             def agg_fn(bufs, wts, protos):
                 return self.agg(bufs, [protos.proto[k] for k in range(w.S)], protos.tcnt, inp["weights"], [w.n] * w.S,
@@ -497,8 +515,10 @@ class Runner:
                     self.step()
                 launches_per_step = lib.fmlp_launch_count() - l0
                 graph = g_
-                graph_note = (f"CUDA-graph replay of the {launches_per_step}-launch round, two-stream DAG "
-                              "{sim,select,fill,loss} || {proto,aggregation}")
+                graph_note = (f"CUDA-graph replay of the {launches_per_step}-launch round, " +
+                              ("three-stream DAG {sim,select,fill,loss} || {proto,tails} || {parameter aggregation}"
+                               if self.agg_stream is not None and (world == 1 or (self.agg is not None and self.agg.split))
+                               else "two-stream DAG {sim,select,fill,loss} || {proto,aggregation}"))
                 for _ in range(3):
                     graph.replay()
             except Exception as exc:          # fall back to eager timing, say so

@@ -175,6 +175,13 @@ __global__ void __launch_bounds__(kQThreads + 32, 1) fedavg_allreduce_q_kernel(c
             }
             __syncwarp();
         };
+        auto flags_ready = [&](int phase, int c) -> bool {         // non-blocking form of wait_flags
+            bool ok = true;
+            if (lane < a.G) ok = (int32_t)(q_ld_acquire_sys(my_flags + q_flag(phase, c, lane)) - epoch) >= 0;
+            ok = __all_sync(0xffffffffu, ok);
+            __syncwarp();
+            return ok;
+        };
         int n = 0;
         uint32_t cur = grab();
         Item ci = decode_item(a, cur);
@@ -184,8 +191,14 @@ __global__ void __launch_bounds__(kQThreads + 32, 1) fedavg_allreduce_q_kernel(c
         while (ci.kind != kItemExit) {
             const uint32_t nxt = grab();
             const Item ni = decode_item(a, nxt);
-            const bool nxt_waits = (ni.kind == kItemReduce || ni.kind == kItemFinal);
-            if (!nxt_waits) publish(n + 1, nxt);                   // prefetch: the compute warps never idle between folds
+            // Prefetch: hand the next item to the compute warps before the current one has been signalled, so
+            // they never idle between items — folds always, reduce items when the peers' partials of that chunk
+            // are already published (the common case: R(c) sits a whole chunk behind F(c) in the list).
+            bool published = false;
+            if (ni.kind == kItemFold || ni.kind == kItemExit || (ni.kind == kItemReduce && flags_ready(0, ni.c))) {
+                publish(n + 1, nxt);
+                published = true;
+            }
             // ---- completion of the current item
             if (lane == 0) {
                 while (q_ld_acquire_cta(&s_done[n & 1]) < kQWarps) { __nanosleep(20); }
@@ -205,9 +218,9 @@ __global__ void __launch_bounds__(kQThreads + 32, 1) fedavg_allreduce_q_kernel(c
                 __syncwarp();   // lane 0's acquire is ordered before the other lanes' release stores
                 if (last && lane < a.G) q_st_release_sys(a.flags[lane] + q_flag(phase, ci.c, a.rank), epoch);
             }
-            // ---- an item that depends on the peers is only handed to the compute warps once its inputs
-            //      are there (never before the previous item has been signalled: no circular waits)
-            if (nxt_waits) {
+            // ---- an item whose inputs are not there yet is only handed over once they are (never before the
+            //      previous item has been signalled: no circular waits between ranks)
+            if (!published) {
                 if (ni.kind == kItemReduce) wait_flags(0, ni.c);
                 else for (int c = 0; c < a.NC; ++c) wait_flags(1, c);
                 publish(n + 1, nxt);

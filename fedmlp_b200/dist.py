@@ -132,7 +132,7 @@ class FusedFedAvgAllReduce:
             raise ValueError(f"1..{cabi.MAX_CLIENTS} clients per rank")
         cabi.require_cuda(*local_bufs)
         for b in local_bufs:
-            if b.numel() != self.P or b.dtype != torch.float32 or not b.is_contiguous():
+            if self.P and (b.numel() != self.P or b.dtype != torch.float32 or not b.is_contiguous()):
                 raise ValueError("client buffers must be contiguous float32 of length P")
         with torch.cuda.device(self.device):
             cabi.check(cabi.lib().fmlp_fedavg_allreduce_f32(
@@ -227,7 +227,7 @@ class QueuedAggregation:
             raise ValueError(f"1..{cabi.MAX_CLIENTS} clients per rank")
         cabi.require_cuda(*local_bufs)
         for b in local_bufs:
-            if b.numel() != self.P or b.dtype != torch.float32 or not b.is_contiguous():
+            if self.P and (b.numel() != self.P or b.dtype != torch.float32 or not b.is_contiguous()):
                 raise ValueError("client buffers must be contiguous float32 of length P")
         tails = None
         if self.T:
@@ -253,43 +253,84 @@ class QueuedAggregation:
 
 class FedMLPAggregation:
     """The whole server aggregation of a FedMLP round (main.py:218-234) for the clients of this rank, across
-    ranks, in three launches: tail pack -> QueuedAggregation -> finalize.  Produces, identically on every rank,
-    the FedAvg parameters (utils/FedAvg.py:7-14), the aggregated prototypes (FedAvg_proto, :72-93), tao
-    (FedAvg_tao, :51-70, float64) and the int64 BatchNorm counters as float32 (FedAvg.py:13)."""
+    ranks: the FedAvg parameters (utils/FedAvg.py:7-14), the aggregated prototypes (FedAvg_proto, :72-93), tao
+    (FedAvg_tao, :51-70, float64) and the int64 BatchNorm counters as float32 (FedAvg.py:13), identical on every
+    rank.  split=False: ONE exchange carries [parameters | prototype sums | fp64 tail] (tail pack -> queue kernel
+    -> finalize).  split=True: the parameters have their own exchange, which only needs the clients' weights and
+    can start at the very beginning of the round on its own stream, and the small tails (2C*D floats + 3C+J
+    doubles) follow the prototype pass in a second, single-chunk launch of the same kernel."""
 
-    def __init__(self, P: int, C: int, D: int, J: int = 0, group=None, device=None, **kw):
+    def __init__(self, P: int, C: int, D: int, J: int = 0, group=None, device=None, split=False, **kw):
         self.C, self.D, self.J = int(C), int(D), int(J)
         self.T = 2 * self.C * self.D
         self.M = 3 * self.C + self.J
-        self.exchange = QueuedAggregation(P, self.T, self.M, group=group, device=device, **kw)
+        self.split = bool(split)
+        if self.split:
+            self.exchange = QueuedAggregation(P, 0, 0, group=group, device=device, **kw)
+            self.tails_exchange = QueuedAggregation(0, self.T, self.M, group=group, device=device, n_chunks=1, max_ctas=8,
+                                                    use_multicast=kw.get("use_multicast"))
+        else:
+            self.exchange = QueuedAggregation(P, self.T, self.M, group=group, device=device, **kw)
+            self.tails_exchange = self.exchange
         dev = self.exchange.device
         self.tail_local = torch.zeros(self.M, dtype=torch.float64, device=dev)
         self.proto = torch.empty(2 * self.C, self.D, dtype=torch.float32, device=dev)
         self.tao = torch.empty(self.C, dtype=torch.float64, device=dev)
         self.counters = torch.empty(max(self.J, 1), dtype=torch.float32, device=dev)
 
+    def _pack(self, tcnt, weights, rows, active, missing, counters, st):
+        K = len(weights)
+        cabi.check(cabi.lib().fmlp_agg_tail_pack_f64(
+            tcnt.data_ptr() if tcnt is not None else None, K, self.C, cabi.f64_array(weights), cabi.i64_array(rows),
+            cabi.u32_array([cabi.class_mask(a) for a in active]), cabi.u32_array([cabi.class_mask(m) for m in missing]),
+            cabi.ptr_array([c.data_ptr() for c in counters]) if self.J else None, self.J,
+            self.tail_local.data_ptr(), st), "fmlp_agg_tail_pack_f64")
+
+    def _finalize(self, psum, f64, total_weight, st):
+        cabi.check(cabi.lib().fmlp_agg_finalize_f32(psum.data_ptr(), f64.data_ptr(), self.C, self.D, self.J, float(total_weight),
+                                                    self.proto.data_ptr(), self.tao.data_ptr(),
+                                                    self.counters.data_ptr() if self.J else None, st), "fmlp_agg_finalize_f32")
+        return self.proto, self.tao, (self.counters[:self.J] if self.J else None)
+
+    def aggregate_params(self, client_flats, weights, total_weight):
+        """split=True: the parameter exchange alone (current stream)."""
+        wn = [float(w) / float(total_weight) for w in weights]
+        params, _, _ = self.exchange(client_flats, wn)
+        return params
+
+    def aggregate_tails(self, client_protos, tcnt, weights, rows, active, missing, total_weight, counters=None):
+        """split=True: prototypes / tao / counters (current stream; after the prototype pass)."""
+        if not self.split:
+            raise RuntimeError("aggregate_tails needs split=True (the combined exchange carries the tails itself)")
+        ex = self.tails_exchange
+        dev = ex.device
+        wn = [float(w) / float(total_weight) for w in weights]
+        tails = [p.reshape(-1) for p in client_protos]
+        with torch.cuda.device(dev):
+            st = cabi.stream_ptr(dev)
+            self._pack(tcnt, weights, rows, active, missing, counters, st)
+            # P == 0: the fp32 vector is the tail alone (the kernel still wants K valid source pointers)
+            _, psum, f64 = ex(tails, wn, tail_bufs=tails, tail_f64=self.tail_local)
+            return self._finalize(psum, f64, total_weight, st)
+
     def __call__(self, client_flats, client_protos, tcnt, weights, rows, active, missing, total_weight, counters=None):
         """client_flats: K fp32 [P]; client_protos: K fp32 [2C, D] (rows of classes the client does not annotate
         are zero, as utils/local_training.py:973-1002 leaves them); tcnt: int32 [K, C] confident counts;
         weights / rows: K client weights (dict_len) and row counts; active / missing: K class lists;
         total_weight: sum of weights over ALL ranks; counters: K int64 [J] tensors or None."""
+        if self.split:
+            params = self.aggregate_params(client_flats, weights, total_weight)
+            proto, tao, cnt = self.aggregate_tails(client_protos, tcnt, weights, rows, active, missing, total_weight, counters)
+            return params, proto, tao, cnt
         ex = self.exchange
-        K = len(client_flats)
-        lib = cabi.lib()
         dev = ex.device
         wn = [float(w) / float(total_weight) for w in weights]
         with torch.cuda.device(dev):
             st = cabi.stream_ptr(dev)
-            cabi.check(lib.fmlp_agg_tail_pack_f64(
-                tcnt.data_ptr() if tcnt is not None else None, K, self.C, cabi.f64_array(weights), cabi.i64_array(rows),
-                cabi.u32_array([cabi.class_mask(a) for a in active]), cabi.u32_array([cabi.class_mask(m) for m in missing]),
-                cabi.ptr_array([c.data_ptr() for c in counters]) if self.J else None, self.J,
-                self.tail_local.data_ptr(), st), "fmlp_agg_tail_pack_f64")
+            self._pack(tcnt, weights, rows, active, missing, counters, st)
             params, psum, f64 = ex(client_flats, wn, tail_bufs=[p.reshape(-1) for p in client_protos], tail_f64=self.tail_local)
-            cabi.check(lib.fmlp_agg_finalize_f32(psum.data_ptr(), f64.data_ptr(), self.C, self.D, self.J, float(total_weight),
-                                                 self.proto.data_ptr(), self.tao.data_ptr(),
-                                                 self.counters.data_ptr() if self.J else None, st), "fmlp_agg_finalize_f32")
-        return params, self.proto, self.tao, (self.counters[:self.J] if self.J else None)
+            proto, tao, cnt = self._finalize(psum, f64, total_weight, st)
+        return params, proto, tao, cnt
 
 
 def FedAvg_distributed(w_local, dict_len_local, group=None, total_weight=None, local_reduce=None):

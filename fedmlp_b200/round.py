@@ -123,7 +123,7 @@ class ClientShard:
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
                        side_stream=None, after_aggregate=None, aggregate_fn=None, counters=None,
-                       aggregate_tails=False) -> RoundResult:
+                       aggregate_tails=False, agg_stream=None, params_fn=None, tails_fn=None) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
@@ -142,6 +142,11 @@ class ClientShard:
         the NCCL path issues its all-reduce there.
         aggregate_fn(client_flats, weights, protos) -> [P] tensor (or a tuple (params, proto_glob, tao,
         counters)): replaces the FedAvg launch altogether (the fused fold + all-reduce kernels of dist.py).
+        agg_stream (with side_stream): three-way split — the parameter aggregation only needs the clients'
+        weights, so it starts at the very beginning of the round on agg_stream, the prototype pass and the small
+        tails run on side_stream, the tagging/loss chain on the current stream.
+        params_fn(client_flats, weights) -> [P] tensor and tails_fn(protos) -> (proto_glob, tao, counters): the
+        multi-GPU exchanges of the split form (dist.FedMLPAggregation(split=True)).
         aggregate_tails / counters: single-GPU aggregation of the small tails of main.py:218-234 next to
         FedAvg — FedAvg_proto (bit-exact kernel), FedAvg_tao (float64) and the int64 BatchNorm counters
         (counters: S int64 tensors of equal length)."""
@@ -188,8 +193,42 @@ class ClientShard:
                 if stream_b is stream:
                     mark("proto")
 
-            def aggregate_stage(stream_b):
+            def params_stage(stream_b):
                 sb = stream_b.cuda_stream
+                if params_fn is not None:
+                    out["glob"] = params_fn(client_flats, weights)
+                    return
+                flags = cabi.FEDAVG_DIVIDE if divide else 0
+                check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
+                                               cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
+                                               sb), "fmlp_fedavg_flat_f32")
+                if after_aggregate is not None:
+                    after_aggregate(glob)
+
+            def tails_stage(stream_b):
+                sb = stream_b.cuda_stream
+                if tails_fn is not None:
+                    out["proto_glob"], out["tao"], out["counters"] = tails_fn(protos)
+                    return
+                if not aggregate_tails:
+                    return
+                J = int(counters[0].numel()) if counters else 0
+                if J > 1024:
+                    raise ValueError("at most 1024 int64 counters")
+                # FedAvg_proto (utils/FedAvg.py:72-93): the bit-exact single-GPU kernel on the clients' prototypes
+                check(lib.fmlp_proto_avg_f32(pl.proto.data_ptr(), S, C, D, 2, cabi.f64_array(weights), pl.class_active,
+                                             pl.proto_glob.data_ptr(), sb), "fmlp_proto_avg_f32")
+                # FedAvg_tao (:51-70, float64) and the int64 counters (:9-13): pack the sums, finalize
+                check(lib.fmlp_agg_tail_pack_f64(pl.tcnt.data_ptr(), S, C, cabi.f64_array(weights), pl.sizes, pl.active,
+                                                 pl.missing, cabi.ptr_array([c.data_ptr() for c in counters]) if J else None,
+                                                 J, pl.tail.data_ptr(), sb), "fmlp_agg_tail_pack_f64")
+                check(lib.fmlp_agg_finalize_f32(None, pl.tail.data_ptr(), C, 0, J, float(divisor), None,
+                                                pl.tao.data_ptr(), pl.counters.data_ptr() if J else None, sb),
+                      "fmlp_agg_finalize_f32")
+                out["proto_glob"], out["tao"] = pl.proto_glob, pl.tao
+                out["counters"] = pl.counters[:J] if J else None
+
+            def aggregate_stage(stream_b):
                 if aggregate_fn is not None:
                     r = aggregate_fn(client_flats, weights, protos)
                     if isinstance(r, tuple):
@@ -197,28 +236,8 @@ class ClientShard:
                     else:
                         out["glob"] = r
                 else:
-                    flags = cabi.FEDAVG_DIVIDE if divide else 0
-                    check(lib.fmlp_fedavg_flat_f32(cabi.ptr_array([b.data_ptr() for b in client_flats]),
-                                                   cabi.f32_array(weights), S, P, float(divisor), flags, glob.data_ptr(),
-                                                   sb), "fmlp_fedavg_flat_f32")
-                    if after_aggregate is not None:
-                        after_aggregate(glob)
-                    if aggregate_tails:
-                        J = int(counters[0].numel()) if counters else 0
-                        if J > 1024:
-                            raise ValueError("at most 1024 int64 counters")
-                        # FedAvg_proto (utils/FedAvg.py:72-93): the bit-exact single-GPU kernel on the clients' prototypes
-                        check(lib.fmlp_proto_avg_f32(pl.proto.data_ptr(), S, C, D, 2, cabi.f64_array(weights), pl.class_active,
-                                                     pl.proto_glob.data_ptr(), sb), "fmlp_proto_avg_f32")
-                        # FedAvg_tao (:51-70, float64) and the int64 counters (:9-13): pack the sums, finalize
-                        check(lib.fmlp_agg_tail_pack_f64(pl.tcnt.data_ptr(), S, C, cabi.f64_array(weights), pl.sizes, pl.active,
-                                                         pl.missing, cabi.ptr_array([c.data_ptr() for c in counters]) if J else None,
-                                                         J, pl.tail.data_ptr(), sb), "fmlp_agg_tail_pack_f64")
-                        check(lib.fmlp_agg_finalize_f32(None, pl.tail.data_ptr(), C, 0, J, float(divisor), None,
-                                                        pl.tao.data_ptr(), pl.counters.data_ptr() if J else None, sb),
-                              "fmlp_agg_finalize_f32")
-                        out["proto_glob"], out["tao"] = pl.proto_glob, pl.tao
-                        out["counters"] = pl.counters[:J] if J else None
+                    params_stage(stream_b)
+                    tails_stage(stream_b)
                 if stream_b is stream:
                     mark("fedavg")
 
@@ -242,7 +261,16 @@ class ClientShard:
                 # then not attributed to the first timed stage
                 check(lib.fmlp_scale_f32(pl.one.data_ptr(), 1, pl.one.data_ptr() + 4, st), "fmlp_scale_f32")
             mark("start")
-            if side_stream is not None:
+            split3 = side_stream is not None and agg_stream is not None and aggregate_fn is None
+            if split3:
+                agg_stream.wait_stream(stream)
+                with torch.cuda.stream(agg_stream):
+                    params_stage(agg_stream)
+                side_stream.wait_stream(stream)
+                with torch.cuda.stream(side_stream):
+                    proto_stage(side_stream)
+                    tails_stage(side_stream)
+            elif side_stream is not None:
                 side_stream.wait_stream(stream)
                 with torch.cuda.stream(side_stream):
                     proto_stage(side_stream)
@@ -254,6 +282,8 @@ class ClientShard:
             if side_stream is not None:
                 select_fill_loss()
                 stream.wait_stream(side_stream)
+                if split3:
+                    stream.wait_stream(agg_stream)
             else:
                 proto_stage(stream)
                 aggregate_stage(stream)

@@ -89,7 +89,7 @@ def _agg_inputs(world, K, P, C, D, J):
     return flats, protos, tcnt, counters, rows, weights, active, missing
 
 
-def _agg_worker(rank, world, port, K, P, C, D, J, n_chunks, multicast, ret):
+def _agg_worker(rank, world, port, K, P, C, D, J, n_chunks, multicast, split, ret):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -99,7 +99,7 @@ def _agg_worker(rank, world, port, K, P, C, D, J, n_chunks, multicast, ret):
         from fedmlp_b200 import dist as fd
         flats, protos, tcnt, counters, rows, weights, active, missing = _agg_inputs(world, K, P, C, D, J)
         mine = list(range(rank * K, (rank + 1) * K))
-        agg = fd.FedMLPAggregation(P, C, D, J, n_chunks=n_chunks, use_multicast=bool(multicast))
+        agg = fd.FedMLPAggregation(P, C, D, J, n_chunks=n_chunks, use_multicast=bool(multicast), split=bool(split))
         outs = []
         for it in range(3):                                   # epochs advance, buffers are reused
             params, proto, tao, cnt = agg([flats[i].cuda() for i in mine], [protos[i].cuda() for i in mine],
@@ -114,16 +114,18 @@ def _agg_worker(rank, world, port, K, P, C, D, J, n_chunks, multicast, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,K,P,C,D,J,n_chunks,multicast", [
-    (1, 3, 4 * 1000, 5, 64, 7, 4, 0), (1, 8, 1 << 20, 5, 1024, 121, 4, 0), (1, 2, 4, 14, 32, 0, 16, 0),
-    (2, 3, 4 * 1000, 5, 64, 7, 4, 0), (2, 3, 4 * 1000, 5, 64, 7, 4, 1), (2, 8, 7042752, 5, 1024, 121, 4, 1),
-    (2, 8, 7042752, 5, 1024, 121, 4, 0), (2, 5, 4 * 7771, 14, 1280, 49, 16, 1), (2, 1, 4, 5, 4, 0, 1, 1)])
-def test_queued_aggregation(lib, world, K, P, C, D, J, n_chunks, multicast):
+@pytest.mark.parametrize("world,K,P,C,D,J,n_chunks,multicast,split", [
+    (1, 3, 4 * 1000, 5, 64, 7, 4, 0, 0), (1, 8, 1 << 20, 5, 1024, 121, 4, 0, 0), (1, 2, 4, 14, 32, 0, 16, 0, 0),
+    (1, 8, 1 << 20, 5, 1024, 121, 4, 0, 1), (1, 3, 4 * 1000, 14, 128, 0, 2, 0, 1),
+    (2, 3, 4 * 1000, 5, 64, 7, 4, 0, 0), (2, 3, 4 * 1000, 5, 64, 7, 4, 1, 0), (2, 8, 7042752, 5, 1024, 121, 4, 1, 0),
+    (2, 8, 7042752, 5, 1024, 121, 4, 0, 0), (2, 5, 4 * 7771, 14, 1280, 49, 16, 1, 0), (2, 1, 4, 5, 4, 0, 1, 1, 0),
+    (2, 8, 7042752, 5, 1024, 121, 4, 1, 1), (2, 5, 4 * 7771, 14, 1280, 49, 8, 0, 1)])
+def test_queued_aggregation(lib, world, K, P, C, D, J, n_chunks, multicast, split):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     from oracle import fedmlp_oracle as O
     ret = mp.Manager().dict()
-    mp.spawn(_agg_worker, args=(world, _free_port(), K, P, C, D, J, n_chunks, multicast, ret), nprocs=world, join=True)
+    mp.spawn(_agg_worker, args=(world, _free_port(), K, P, C, D, J, n_chunks, multicast, split, ret), nprocs=world, join=True)
     flats, protos, tcnt, counters, rows, weights, active, missing = _agg_inputs(world, K, P, C, D, J)
     n = K * world
     acc = flats[0].double() * weights[0]
