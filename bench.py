@@ -75,8 +75,9 @@ def parse_args():
                          "from the start of the round + a second single-chunk launch for the packed tails after the prototype pass "
                          "(default); queue = one exchange for parameters + tails; fused_r01 = the round-1 cooperative peer-store "
                          "kernel (parameters only); nccl = local fold + NCCL all-reduce (parameters only)")
-    ap.add_argument("--streams", type=int, default=3, choices=[2, 3],
-                    help="3: tagging/loss chain || prototypes + tails || parameter aggregation; 2: the last two share a stream")
+    ap.add_argument("--streams", type=int, default=0, choices=[0, 2, 3],
+                    help="3: tagging/loss chain || prototypes + tails || parameter aggregation; 2: the last two share a stream; "
+                         "0 = auto (2 on one GPU, where all three chains are HBM-bound; 3 with a collective)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     return ap.parse_args()
 
@@ -367,7 +368,8 @@ class Runner:
         self.shard.loss_variant = cabi.LOSS2_SUP_DIS if w.loss == "sup_dis" else cabi.LOSS2_SUP
         self.fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
         self.side_stream = torch.cuda.Stream(device=dev)
-        self.agg_stream = torch.cuda.Stream(device=dev) if a.streams == 3 else None
+        n_streams = a.streams or (2 if world == 1 else 3)
+        self.agg_stream = torch.cuda.Stream(device=dev) if n_streams == 3 else None
         self.total_w = float(sum(inp["weights"]) * world)
         self.w_norm = [x / self.total_w for x in inp["weights"]]          # pre-normalised: the all-reduce yields the mean
         self.agg = self.fused = None
@@ -394,11 +396,11 @@ class Runner:
                 self.collective += f" (requested '{a.collective}' unavailable: {type(exc).__name__}: {exc})"[:240]
         self.dist = dist
 
-    def step(self, timers=None, overlap=True, data=None):
+    def step(self, timers=None, overlap=True, data=None, only=None):
         """One round hot path.  overlap: {prototypes -> aggregation} on a side stream, concurrent with
         {sim -> select -> fill -> loss}; the per-stage event timing (timers) runs the stages back to back on one
         stream so every kernel is timed alone."""
-        side = self.side_stream if (overlap and timers is None) else None
+        side = self.side_stream if (overlap and timers is None and only is None) else None
         aggs = self.agg_stream if side is not None else None
         inp = data if data is not None else self.inp
         sh, w = self.shard, self.w
@@ -406,7 +408,7 @@ class Runner:
                 inp["logits_proto"], inp["flats"])
         if self.world == 1:
             return sh.round_hot_path(*args, inp["weights"], timers=timers, fedavg_out=self.fed_out, side_stream=side,
-                                     agg_stream=aggs, aggregate_tails=True, counters=inp["counters"])
+                                     agg_stream=aggs, aggregate_tails=True, counters=inp["counters"], only=only)
         if self.agg is not None and self.agg.split:
             def params_fn(bufs, wts):
                 return self.agg.aggregate_params(bufs, inp["weights"], self.total_w)
@@ -415,18 +417,18 @@ class Runner:
                 return self.agg.aggregate_tails([protos.proto[k] for k in range(w.S)], protos.tcnt, inp["weights"], [w.n] * w.S,
                                                 sh.active, sh.missing, self.total_w, inp["counters"])
             return sh.round_hot_path(*args, self.w_norm, timers=timers, fedavg_out=self.fed_out, divide=False,
-                                     side_stream=side, agg_stream=aggs, params_fn=params_fn, tails_fn=tails_fn)
+                                     side_stream=side, agg_stream=aggs, params_fn=params_fn, tails_fn=tails_fn, only=only)
         if self.agg is not None:
             def agg_fn(bufs, wts, protos):
                 return self.agg(bufs, [protos.proto[k] for k in range(w.S)], protos.tcnt, inp["weights"], [w.n] * w.S,
                                 sh.active, sh.missing, self.total_w, inp["counters"])
             return sh.round_hot_path(*args, self.w_norm, timers=timers, fedavg_out=self.fed_out, divide=False,
-                                     side_stream=side, aggregate_fn=agg_fn)
+                                     side_stream=side, aggregate_fn=agg_fn, only=only)
         if self.fused is not None:
             return sh.round_hot_path(*args, self.w_norm, timers=timers, fedavg_out=self.fed_out, divide=False,
-                                     side_stream=side, aggregate_fn=lambda bufs, wts, protos: self.fused(bufs, wts))
+                                     side_stream=side, aggregate_fn=lambda bufs, wts, protos: self.fused(bufs, wts), only=only)
         return sh.round_hot_path(*args, self.w_norm, timers=timers, fedavg_out=self.fed_out, divide=False,
-                                 side_stream=side, after_aggregate=lambda g: self.dist.all_reduce(g))
+                                 side_stream=side, after_aggregate=lambda g: self.dist.all_reduce(g), only=only)
 
     # ---- untimed parity gate for the multi-GPU exchange -------------------------------------------------
     def parity(self):
@@ -587,13 +589,49 @@ class Runner:
             serial_ms_step = eb0.elapsed_time(eb1) / steps
             results = [{q: e[p].elapsed_time(e[q]) for p, q in zip(order[:-1], order[1:])} for e in raw]
 
-        kms = {k: statistics.median(r[k] for r in results) for k in order[1:]}
+        in_round = {k: statistics.median(r[k] for r in results) for k in order[1:]}
+        # ---- timed region C (roofline): every streaming stage's launches back to back on the main stream — a
+        #      CUDA graph holding that stage alone is replayed K times between two events (eager launches when
+        #      graphs are off), so the launch latency of one replay hides behind the previous one exactly as
+        #      between the kernels of the real round.  Region B brackets every stage with event nodes, which puts
+        #      each stage's launch latency (~6-9 us) inside its own interval; both are reported.  Inputs of every
+        #      stage (>= 225 MB) exceed the 126 MB L2, so no flush is needed between the launches.
+        kms = dict(in_round)
+        loop_note = "not measured"
+        reps = max(20, min(steps, 200))
+        for k in ("sim", "proto", "fedavg"):
+            try:
+                g3 = None
+                if graph is not None:
+                    g3 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g3):
+                        self.step(only=k)
+                run_once = (g3.replay if g3 is not None else (lambda k=k: self.step(only=k)))
+                for _ in range(3):
+                    run_once()
+                self.fence()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for _ in range(reps):
+                    run_once()
+                c1.record()
+                self.fence()
+                tk = torch.tensor([c0.elapsed_time(c1) / reps], dtype=torch.float64, device=dev)
+                if world > 1:
+                    self.dist.all_reduce(tk, op=self.dist.ReduceOp.MAX)
+                kms[k] = float(tk.item())
+                loop_note = (f"{reps} back-to-back " + ("replays of a CUDA graph holding the stage alone" if g3 is not None else "eager launches")
+                             + " between two CUDA events, per stage")
+            except Exception as exc:
+                loop_note = f"stage loop failed ({type(exc).__name__}: {exc})"[:160] + "; in-round event brackets used"
+                torch.cuda.synchronize()
         ab = alg_bytes(w, inp)
         peak, peak_src = peak_hbm()
         kernels = {}
         for k in ("sim", "proto", "fedavg", "loss", "select_fill"):
             gbs = ab[k] / (kms[k] * 1e-3) / 1e9
-            kernels[k] = {"ms": round(kms[k], 5), "alg_bytes": ab[k], "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+            kernels[k] = {"ms": round(kms[k], 5), "alg_bytes": ab[k], "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4),
+                          "ms_in_round_between_event_nodes": round(in_round[k], 5)}
         kernels["fedavg"]["includes"] = "FedAvg + FedAvg_proto + tail pack + finalize launches" if world == 1 else self.collective
         if world > 1:
             link_bytes = 2 * (world - 1) / world * 4 * inp["Ppad"]
@@ -607,7 +645,8 @@ class Runner:
                     "peak_source": peak_src, "alg_bytes_per_launch": ab[dom], "avg_launch_ms": round(kms[dom], 5)}
         stream_bytes = ab["sim"] + ab["proto"] + ab["fedavg"] + ab["loss"] + ab["select_fill"]
         return dict(ms_per_step=ms_step, value=inp["N"] * world / (ms_step * 1e-3), kernels=kernels, roofline=roofline,
-                    launches=int(launches), launches_per_step=launches_per_step, graph_note=graph_note, stage_note=stage_note,
+                    launches=int(launches), launches_per_step=launches_per_step, graph_note=graph_note,
+                    stage_note=f"ms: {loop_note}; ms_in_round_between_event_nodes: {stage_note}",
                     serial_ms_per_step=serial_ms_step, step_alg_bytes=stream_bytes,
                     step_frac_of_hbm_peak=round(stream_bytes / (ms_step * 1e-3) / 1e9 / peak, 4), graph=graph)
 

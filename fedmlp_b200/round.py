@@ -123,7 +123,7 @@ class ClientShard:
     def round_hot_path(self, feat_tag, proto_glob, logits, logits_glob, labels, feat_proto, logits_proto,
                        client_flats, weights, timers=None, fedavg_out=None, divide=True, divisor=None,
                        side_stream=None, after_aggregate=None, aggregate_fn=None, counters=None,
-                       aggregate_tails=False, agg_stream=None, params_fn=None, tails_fn=None) -> RoundResult:
+                       aggregate_tails=False, agg_stream=None, params_fn=None, tails_fn=None, only=None) -> RoundResult:
         """feat_tag [N, D]: features of the incoming global model (tagging, :1026-1049);
         logits / logits_glob [N, C]: student / frozen-global logits for the loss (:1178-1188);
         feat_proto / logits_proto: features and logits of the locally trained model (:1223-1239);
@@ -147,6 +147,8 @@ class ClientShard:
         tails run on side_stream, the tagging/loss chain on the current stream.
         params_fn(client_flats, weights) -> [P] tensor and tails_fn(protos) -> (proto_glob, tao, counters): the
         multi-GPU exchanges of the split form (dist.FedMLPAggregation(split=True)).
+        only: "sim" | "proto" | "fedavg" | "tail" — launch just that stage on the current stream (bench.py times
+        each stage's launches back to back this way).
         aggregate_tails / counters: single-GPU aggregation of the small tails of main.py:218-234 next to
         FedAvg — FedAvg_proto (bit-exact kernel), FedAvg_tao (float64) and the int64 BatchNorm counters
         (counters: S int64 tensors of equal length)."""
@@ -260,6 +262,15 @@ class ClientShard:
                 # a one-element kernel in front of the first event: the launch latency of the graph itself is
                 # then not attributed to the first timed stage
                 check(lib.fmlp_scale_f32(pl.one.data_ptr(), 1, pl.one.data_ptr() + 4, st), "fmlp_scale_f32")
+            def sim_stage():
+                check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
+                                           tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], pl.ws_sim.data_ptr(),
+                                           pl.ws_sim.numel(), st), "fmlp_tag_sim_f32")
+
+            if only is not None:
+                {"sim": sim_stage, "proto": lambda: proto_stage(stream), "fedavg": lambda: aggregate_stage(stream),
+                 "tail": select_fill_loss}[only]()
+                return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz, protos, out["glob"], ev)
             mark("start")
             split3 = side_stream is not None and agg_stream is not None and aggregate_fn is None
             if split3:
@@ -275,9 +286,7 @@ class ClientShard:
                 with torch.cuda.stream(side_stream):
                     proto_stage(side_stream)
                     aggregate_stage(side_stream)
-            check(lib.fmlp_tag_sim_f32(feat_tag.data_ptr(), D, D, proto_glob.data_ptr(), C, S, pl.rows, pl.missing,
-                                       tg.sim.data_ptr(), tg.sim.shape[1], SIM_MODES[self.sim_mode], pl.ws_sim.data_ptr(),
-                                       pl.ws_sim.numel(), st), "fmlp_tag_sim_f32")
+            sim_stage()
             mark("sim")
             if side_stream is not None:
                 select_fill_loss()

@@ -57,6 +57,8 @@ except Exception as exc:
 torch.cuda.empty_cache()
 settings = [(mc, nc, fi, ri, ctas) for mc in (1, 0) for nc in (2, 4, 8) for (fi, ri) in ((2, 2), (2, 1), (4, 2), (4, 4)) for ctas in (0,)]
 settings += [(1, 4, 2, 2, 96), (1, 4, 2, 2, 64), (1, 1, 2, 2, 0), (1, 16, 2, 2, 0)]
+if os.environ.get("FMLP_SWEEP_SHORT"):
+    settings = [(mc, nc, fi, ri, 0) for mc in (1, 0) for nc in (2, 4, 8) for (fi, ri) in ((2, 2), (4, 4))] + [(1, 1, 2, 2, 0), (1, 4, 8, 8, 0)]
 for mc, nc, fi, ri, ctas in settings:
     try:
         q = fd.QueuedAggregation(P, T, M, device=dev, n_chunks=nc, use_multicast=bool(mc), fold_iters=fi, red_iters=ri, max_ctas=ctas)
