@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"
+import os as _os
+
+# FEDMLP_B200_LIB: alternative build of the same library (tuning experiments under tools/); the default is in-tree
+LIB_PATH = Path(_os.environ.get("FEDMLP_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"))
 
 ABI_VERSION = 3
 MAX_CLASSES = 32

@@ -40,7 +40,11 @@ constexpr int kQMaxChunks = FMLP_AR_MAX_CHUNKS;
 #ifndef FMLP_ARQ_THREADS
 #define FMLP_ARQ_THREADS 1024
 #endif
+#ifndef FMLP_ARQ_CTAS_PER_SM
+#define FMLP_ARQ_CTAS_PER_SM 1
+#endif
 constexpr int kQThreads = FMLP_ARQ_THREADS - 32;      // compute threads per CTA (+ one signal / scheduler warp)
+constexpr int kQCtasPerSm = FMLP_ARQ_CTAS_PER_SM;
 constexpr int kQWarps = kQThreads / 32;
 constexpr int kQUnroll = 8;
 
@@ -138,7 +142,7 @@ __device__ __forceinline__ Item decode_item(const QArgs& a, uint32_t idx) {
 }
 
 template <bool NVLS>
-__global__ void __launch_bounds__(kQThreads + 32, 1) fedavg_allreduce_q_kernel(const __grid_constant__ QArgs a) {
+__global__ void __launch_bounds__(kQThreads + 32, kQCtasPerSm) fedavg_allreduce_q_kernel(const __grid_constant__ QArgs a) {
     __shared__ int s_item[2];       // published item index per slot
     __shared__ int s_ready[2];      // sequence number of the item in the slot (n + 1)
     __shared__ int s_done[2];       // compute warps that finished the slot's item
@@ -442,7 +446,7 @@ extern "C" int fmlp_fedavg_allreduce_q_f32(const float* const* srcs, const float
     }
     const int sms = sm_count();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
-    int blocks = sms;
+    int blocks = sms * kQCtasPerSm;
     if (max_ctas > 0 && max_ctas < blocks) blocks = max_ctas;
     a.mc_partial = mc_partial; a.mc_result = mc_result;
     a.tail_src = tail_f64; a.M = M;
