@@ -359,17 +359,24 @@ template <int NPAIR, bool FOLD>
 static int launch_sim(SimArgs& a, const SimFeat& ft, cudaStream_t st) {
     using Cfg = SimCfg<NPAIR, FOLD>;
     const size_t fixed = ((size_t)a.NG * 32 * Cfg::NV + (size_t)Cfg::W * Cfg::PV * Cfg::ROWS + ((2 * NPAIR + 3) & ~3)) * sizeof(float);
-    const size_t budget = 227u * 1024u;
+    // Ring depth: as many stages as fit in `soft` — 200 KB, not the full 227 KB, so that a CTA of a concurrent
+    // kernel with a little shared memory (the aggregation kernels of the other streams) can still share the SM;
+    // a launch whose fixed part alone needs more falls back to two stages within the hard limit.
+    const size_t hard = 227u * 1024u;
     static int max_stages = 0;
+    static size_t soft = 0;
     if (max_stages == 0) {
         max_stages = 8;
+        soft = 200u * 1024u;
         if (const char* e = getenv("FMLP_SIM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 16) max_stages = v; }
+        if (const char* e = getenv("FMLP_SIM_SMEM_KB")) { int v = atoi(e); if (v >= 64 && v <= 227) soft = (size_t)v * 1024u; }
     }
+    size_t budget = soft;
     int S = max_stages;
     auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + ((size_t)Cfg::W * s + 2) * sizeof(uint64_t); };   // ring barriers + the table barrier
     while (S > 2 && smem_of(S) > budget) --S;
     const size_t smem = smem_of(S);
-    if (smem > budget) return FMLP_ERR_UNSUPPORTED;
+    if (smem > hard) return FMLP_ERR_UNSUPPORTED;
     a.S = S;
     auto kern = tag_sim_kernel<NPAIR, FOLD>;
     static size_t configured = 0;  // per template instance
