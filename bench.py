@@ -369,7 +369,10 @@ class Runner:
         self.fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
         self.side_stream = torch.cuda.Stream(device=dev)
         n_streams = a.streams or (2 if world == 1 else 3)
-        self.agg_stream = torch.cuda.Stream(device=dev) if n_streams == 3 else None
+        # the parameter exchange gets a HIGH-priority stream: its (persistent, small-footprint) CTAs must be placed
+        # before the prototype / similarity kernels of the other streams fill every SM's register file
+        prio = int(os.environ.get("FMLP_AGG_PRIORITY", "-1"))
+        self.agg_stream = torch.cuda.Stream(device=dev, priority=prio) if n_streams == 3 else None
         self.total_w = float(sum(inp["weights"]) * world)
         self.w_norm = [x / self.total_w for x in inp["weights"]]          # pre-normalised: the all-reduce yields the mean
         self.agg = self.fused = None

@@ -7,14 +7,15 @@ run() { # tag, env...
   env "$@" timeout 200 $B > gpurun_out/bench_var3_${N}gpu_$tag.json 2> gpurun_out/bench_var3_${N}gpu_$tag.err; echo "$tag rc=$?"
 }
 rm -f gpurun_out/bench_var3_${N}gpu_*.json
+L2=$PWD/tools/bin/lib_arq_t288x4.so
+L5=$PWD/tools/bin/lib_arq_t544x2.so
+run t544_c148_mc0 FEDMLP_B200_LIB=$L5 FMLP_ARQ_CTAS=148 FMLP_ARQ_MULTICAST=0
+run t544_c148_mc0_noprio FEDMLP_B200_LIB=$L5 FMLP_ARQ_CTAS=148 FMLP_ARQ_MULTICAST=0 FMLP_AGG_PRIORITY=0
+run t544_c296_mc0 FEDMLP_B200_LIB=$L5 FMLP_ARQ_MULTICAST=0
+run t288_c296_mc0 FEDMLP_B200_LIB=$L2 FMLP_ARQ_CTAS=296 FMLP_ARQ_MULTICAST=0
+run t288_c444_mc0 FEDMLP_B200_LIB=$L2 FMLP_ARQ_CTAS=444 FMLP_ARQ_MULTICAST=0
+run t544_c148_mc1 FEDMLP_B200_LIB=$L5 FMLP_ARQ_CTAS=148 FMLP_ARQ_MULTICAST=1
 run default_mc0 FMLP_ARQ_MULTICAST=0
-run default_mc1 FMLP_ARQ_MULTICAST=1
-L=$PWD/tools/bin/lib_arq_t288x4.so
-run t288_c296_mc0 FEDMLP_B200_LIB=$L FMLP_ARQ_CTAS=296 FMLP_ARQ_MULTICAST=0
-run t288_c444_mc0 FEDMLP_B200_LIB=$L FMLP_ARQ_CTAS=444 FMLP_ARQ_MULTICAST=0
-run t288_c592_mc0 FEDMLP_B200_LIB=$L FMLP_ARQ_MULTICAST=0
-run t288_c444_mc1 FEDMLP_B200_LIB=$L FMLP_ARQ_CTAS=444 FMLP_ARQ_MULTICAST=1
-run t544_c296_mc0 FEDMLP_B200_LIB=$PWD/tools/bin/lib_arq_t544x2.so FMLP_ARQ_MULTICAST=0
 python - <<PY
 import json,glob
 for f in sorted(glob.glob('gpurun_out/bench_var3_${N}gpu_*.json')):
