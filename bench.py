@@ -70,7 +70,7 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--collective", default="queue_split", choices=["queue_split", "queue", "fused_r01", "nccl"],
+    ap.add_argument("--collective", default="queue_split", choices=["queue_split", "push_split", "queue", "fused_r01", "nccl"],
                     help="N>1: queue_split = work-queue fold + NVLS/P2P all-reduce kernel for the parameters on its own stream "
                          "from the start of the round + a second single-chunk launch for the packed tails after the prototype pass "
                          "(default); queue = one exchange for parameters + tails; fused_r01 = the round-1 cooperative peer-store "
@@ -380,7 +380,13 @@ class Runner:
         if world > 1:
             self.collective = "nccl all_reduce after the local fold (parameters only)"
             try:
-                if a.collective in ("queue", "queue_split"):
+                if a.collective == "push_split":
+                    from fedmlp_b200.dist import FedMLPAggregation
+                    self.agg = FedMLPAggregation(inp["Ppad"], C, w.D, inp["J"], device=dev, split=True, params_impl="push")
+                    self.collective = (f"parameters: fold + two-shot all-reduce by posted peer stores in one kernel ({self.agg.exchange.n_chunks} "
+                                       "chunks) on its own high-priority stream from the start of the round; prototype sums + fp64 tail: "
+                                       f"work-queue kernel ({self.agg.tails_exchange.path}), one chunk, after the prototype pass")
+                elif a.collective in ("queue", "queue_split"):
                     from fedmlp_b200.dist import FedMLPAggregation
                     self.agg = FedMLPAggregation(inp["Ppad"], C, w.D, inp["J"], device=dev, split=(a.collective == "queue_split"))
                     ex = self.agg.exchange

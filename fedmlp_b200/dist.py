@@ -260,12 +260,19 @@ class FedMLPAggregation:
     can start at the very beginning of the round on its own stream, and the small tails (2C*D floats + 3C+J
     doubles) follow the prototype pass in a second, single-chunk launch of the same kernel."""
 
-    def __init__(self, P: int, C: int, D: int, J: int = 0, group=None, device=None, split=False, **kw):
+    def __init__(self, P: int, C: int, D: int, J: int = 0, group=None, device=None, split=False, params_impl="queue", **kw):
+        """params_impl (split=True only): "queue" = the work-queue kernel, "push" = the round-1 peer-store kernel
+        (FusedFedAvgAllReduce: cooperative launch, reduce-scatter by posted peer stores)."""
         self.C, self.D, self.J = int(C), int(D), int(J)
         self.T = 2 * self.C * self.D
         self.M = 3 * self.C + self.J
         self.split = bool(split)
-        if self.split:
+        self.params_impl = params_impl if self.split else "queue"
+        if self.split and self.params_impl == "push":
+            self.exchange = FusedFedAvgAllReduce(P, group=group, device=device)
+            self.tails_exchange = QueuedAggregation(0, self.T, self.M, group=group, device=device, n_chunks=1, max_ctas=8,
+                                                    use_multicast=kw.get("use_multicast"))
+        elif self.split:
             self.exchange = QueuedAggregation(P, 0, 0, group=group, device=device, **kw)
             self.tails_exchange = QueuedAggregation(0, self.T, self.M, group=group, device=device, n_chunks=1, max_ctas=8,
                                                     use_multicast=kw.get("use_multicast"))
@@ -295,6 +302,8 @@ class FedMLPAggregation:
     def aggregate_params(self, client_flats, weights, total_weight):
         """split=True: the parameter exchange alone (current stream)."""
         wn = [float(w) / float(total_weight) for w in weights]
+        if self.params_impl == "push":
+            return self.exchange(client_flats, wn)
         params, _, _ = self.exchange(client_flats, wn)
         return params
 
