@@ -116,6 +116,15 @@ __device__ __forceinline__ void mm_st_f64(double* mc, double v) {
     asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
 }
 
+#ifdef FMLP_ARQ_TRACE
+// Debug build (tools/build_arq_variants.sh): per-CTA item timeline, 4 x u64 per record
+//   [item index | kind<<32 | c<<40, t_published, t_done_observed, t_signalled]  (globaltimer ns)
+constexpr int kTraceMax = 1 << 16;
+__device__ unsigned long long g_trace[kTraceMax][4];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 // Item encoding: kind in the top bits.
 enum : int { kItemFold = 0, kItemReduce = 1, kItemFinal = 2, kItemExit = 3 };
 struct Item { int kind, c, j; };
@@ -192,6 +201,9 @@ __global__ void __launch_bounds__(kQThreads + 32, kQCtasPerSm) fedavg_allreduce_
         if (ci.kind == kItemReduce) wait_flags(0, ci.c);
         if (ci.kind == kItemFinal) for (int c = 0; c < a.NC; ++c) wait_flags(1, c);
         publish(0, cur);
+#ifdef FMLP_ARQ_TRACE
+        unsigned long long t_pub_cur = gtime(), t_pub_nxt = 0;
+#endif
         while (ci.kind != kItemExit) {
             const uint32_t nxt = grab();
             const Item ni = decode_item(a, nxt);
@@ -202,6 +214,9 @@ __global__ void __launch_bounds__(kQThreads + 32, kQCtasPerSm) fedavg_allreduce_
             if (ni.kind == kItemFold || ni.kind == kItemExit || (ni.kind == kItemReduce && flags_ready(0, ni.c))) {
                 publish(n + 1, nxt);
                 published = true;
+#ifdef FMLP_ARQ_TRACE
+                t_pub_nxt = gtime();
+#endif
             }
             // ---- completion of the current item
             if (lane == 0) {
@@ -209,6 +224,9 @@ __global__ void __launch_bounds__(kQThreads + 32, kQCtasPerSm) fedavg_allreduce_
                 s_done[n & 1] = 0;
             }
             __syncwarp();
+#ifdef FMLP_ARQ_TRACE
+            const unsigned long long t_done = gtime();
+#endif
             if (ci.kind != kItemFinal) {
                 const int phase = ci.kind == kItemFold ? 0 : 1;
                 const uint32_t need = (uint32_t)(phase == 0 ? a.FJ : a.RJ);
@@ -224,11 +242,26 @@ __global__ void __launch_bounds__(kQThreads + 32, kQCtasPerSm) fedavg_allreduce_
             }
             // ---- an item whose inputs are not there yet is only handed over once they are (never before the
             //      previous item has been signalled: no circular waits between ranks)
+#ifdef FMLP_ARQ_TRACE
+            if (lane == 0) {
+                const unsigned int slot = atomicAdd(&g_trace_n, 1u);
+                if (slot < kTraceMax) {
+                    g_trace[slot][0] = (unsigned long long)cur | ((unsigned long long)ci.kind << 32) | ((unsigned long long)ci.c << 40) | ((unsigned long long)blockIdx.x << 48);
+                    g_trace[slot][1] = t_pub_cur; g_trace[slot][2] = t_done; g_trace[slot][3] = gtime();
+                }
+            }
+#endif
             if (!published) {
                 if (ni.kind == kItemReduce) wait_flags(0, ni.c);
                 else for (int c = 0; c < a.NC; ++c) wait_flags(1, c);
                 publish(n + 1, nxt);
+#ifdef FMLP_ARQ_TRACE
+                t_pub_nxt = gtime();
+#endif
             }
+#ifdef FMLP_ARQ_TRACE
+            t_pub_cur = t_pub_nxt;
+#endif
             cur = nxt; ci = ni; ++n;
         }
         if (lane == 0) {
@@ -515,3 +548,18 @@ extern "C" int fmlp_agg_finalize_f32(const float* proto_sum, const double* tail,
                                                                                       proto_out, tao_out, counters_out);
     return launch_status();
 }
+
+#ifdef FMLP_ARQ_TRACE
+// debug only: copies the trace to the host (synchronises) and resets it; returns the number of records
+extern "C" int fmlp_arq_trace_dump(unsigned long long* out, int max_records) {
+    unsigned int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+    if ((int)n > max_records) n = max_records;
+    if (n > (unsigned)kTraceMax) n = kTraceMax;
+    cudaMemcpyFromSymbol(out, g_trace, (size_t)n * 4 * sizeof(unsigned long long));
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+    return (int)n;
+}
+#endif

@@ -12,3 +12,7 @@ for v in "t544x2:-DFMLP_ARQ_THREADS=544 -DFMLP_ARQ_CTAS_PER_SM=2" "t288x4:-DFMLP
 done
 wait
 ls -la tools/bin/*.so
+# trace build (per-item timeline, tools/arq_trace.py)
+nvcc $FLAGS -DFMLP_ARQ_TRACE -c fedmlp_b200/csrc/fedavg_allreduce_q.cu -o /tmp/arqv/arq_trace.o
+objs=$(ls fedmlp_b200/build/*.o | grep -v fedavg_allreduce_q.o)
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xlinker --exclude-libs=ALL -Xlinker -Bsymbolic -o tools/bin/lib_arq_trace.so $objs /tmp/arqv/arq_trace.o
