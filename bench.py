@@ -70,8 +70,10 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--collective", default="queue_split", choices=["queue_split", "push_split", "queue", "fused_r01", "nccl"],
-                    help="N>1: queue_split = work-queue fold + NVLS/P2P all-reduce kernel for the parameters on its own stream "
+    ap.add_argument("--collective", default="auto", choices=["auto", "queue_split", "push_split", "queue", "fused_r01", "nccl"],
+                    help="N>1: auto = push_split up to 4 GPUs, queue_split (NVLS) beyond — the measured best of each "
+                         "(profiles/r02_multi_gpu_variants.txt); push_split = the parameters through the fold + two-shot peer-store kernel "
+                         "on its own stream, the packed tails through the work-queue kernel; queue_split = work-queue fold + NVLS/P2P all-reduce kernel for the parameters on its own stream "
                          "from the start of the round + a second single-chunk launch for the packed tails after the prototype pass "
                          "(default); queue = one exchange for parameters + tails; fused_r01 = the round-1 cooperative peer-store "
                          "kernel (parameters only); nccl = local fold + NCCL all-reduce (parameters only)")
@@ -379,6 +381,8 @@ class Runner:
         self.collective = "none (single GPU: FedAvg + FedAvg_proto + FedAvg_tao + counter kernels)"
         if world > 1:
             self.collective = "nccl all_reduce after the local fold (parameters only)"
+            if a.collective == "auto":
+                a.collective = "push_split" if world <= 4 else "queue_split"
             try:
                 if a.collective == "push_split":
                     from fedmlp_b200.dist import FedMLPAggregation
@@ -738,6 +742,13 @@ def gpu_arm(a):
             e2e = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
             torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    api = None
+    if world == 1 and not a.skip_e2e:
+        try:
+            api = measure_api(w, dev)
+        except Exception as exc:
+            api = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.synchronize()
 
     # ---- the other BASELINE configs at this N (C = 14 shapes), fewer steps, no e2e / CPU leg
     extra = []
@@ -802,6 +813,7 @@ def gpu_arm(a):
             "step_frac_of_hbm_peak": headline["step_frac_of_hbm_peak"],
             "timing": {"value": headline["graph_note"], "kernels": headline["stage_note"],
                        "serial_ms_per_step": headline["serial_ms_per_step"]},
+            "api": api,
             "parity": parity, "parity_ok": (parity or {}).get("parity_ok") if world > 1 else None,
             "numa": numa, "configs": extra,
         }
@@ -813,6 +825,49 @@ def gpu_arm(a):
 
 
 headline_collective = None
+
+
+def measure_api(w: Workload, dev, reps=10):
+    """The reference-shaped entry points as a caller uses them (wall clock around the call + a device sync, median
+    of `reps`): FedAvg(w_locals, dict_len) (utils/FedAvg.py:7-14) on K real-layout state_dicts — 727 separately
+    allocated CUDA tensors each (what main.py:196 collects), FlatStateDicts (fedmlp_b200.flat), and CPU tensors
+    (the reference's stage 2 returns net.cpu() weights, local_training.py:1251) — and one tagging pass of a client
+    through TagBatch.step (similarity + selection, :1052-1112)."""
+    import torch
+    import fedmlp_b200 as F
+    from fedmlp_b200.shapes import synth_state_dict
+
+    shapes = w.state_shapes()
+    K = 8
+    base = synth_state_dict(shapes, 1037)
+    cpu_sds = [synth_state_dict(shapes, 1038 + k, base=base, counter=100 + k) for k in range(K)]
+    gpu_sds = [type(sd)((k, v.to(dev)) for k, v in sd.items()) for sd in cpu_sds]
+    flat_sds = [F.FlatStateDict.from_state_dict(sd) for sd in gpu_sds]
+    dict_len = [w.n] * K
+
+    def wall(fn):
+        ts = []
+        for _ in range(reps + 2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return round(statistics.median(ts[2:]), 4)
+
+    out = {"fedavg_state_dicts_ms": wall(lambda: F.FedAvg(gpu_sds, dict_len)),
+           "fedavg_flat_state_dicts_ms": wall(lambda: F.FedAvg(flat_sds, dict_len)),
+           "fedavg_cpu_state_dicts_ms": wall(lambda: F.FedAvg(cpu_sds, dict_len)),
+           "tensors_per_state_dict": len(shapes), "clients": K}
+    n, C, D = w.n, w.C, w.D
+    g = torch.Generator(device=dev).manual_seed(3)
+    feat = torch.relu(torch.randn(n, D, generator=g, device=dev))
+    proto = torch.relu(torch.randn(2 * C, D, generator=g, device=dev)) + 0.05
+    tb = F.TagBatch([0, n], C, [[0]], [list(range(1, C))], device=dev)
+    out["train_FedMLP_tag_ms"] = wall(lambda: tb.step(feat, proto, 0.005, 0.01, mode="folded"))
+    out["note"] = ("wall clock incl. Python + a device sync; scattered dicts: one pointer-table pass over 727 x K tensors per call "
+                   "(table re-uploaded only when a pointer changed); CPU dicts: pinned staging (pooled) + H2D + D2H of the result")
+    return out
 
 
 def run_e2e(a, run, graph, numa):

@@ -34,7 +34,9 @@ namespace fmlp {
 constexpr int kArMaxRanks = 8;
 constexpr int kArMaxChunks = FMLP_AR_MAX_CHUNKS;
 #ifndef FMLP_AR_THREADS
-#define FMLP_AR_THREADS 992
+#define FMLP_AR_THREADS 480   // round 2: half an SM's threads and register file, so that the kernel shares the SMs with the
+                              // similarity / prototype kernels of the other streams (992 = the whole SM: 0.192 -> 0.185 ms
+                              // per round at 2 GPUs, 0.212 -> 0.206 at 8, profiles/r02_multi_gpu_variants.txt)
 #endif
 constexpr int kArThreads = FMLP_AR_THREADS;   // compute threads per CTA (+ one signal warp); one CTA per SM: every CTA's
                                               // per-chunk release costs its SM ~1 us, so fewer, larger CTAs
@@ -258,10 +260,11 @@ extern "C" int fmlp_fedavg_allreduce_f32(const float* const* srcs, const float* 
         int b = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fedavg_allreduce_kernel, kArThreads + 32, 0);
         if (e != cudaSuccess) return (int)e;
-        per_sm = b < 1 ? 1 : (b > 4 ? 4 : b);
+        per_sm = 1;   // one CTA per SM (see FMLP_AR_THREADS); FMLP_AR_CTAS_PER_SM raises it up to the occupancy limit
+        (void)b;
         // tuning knob: a smaller footprint leaves SM resources to the concurrent tagging/prototype
         // kernels during the NVLink-bound phases
-        if (const char* e = getenv("FMLP_AR_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+        if (const char* e = getenv("FMLP_AR_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= b && v <= 4) per_sm = v; }
     }
     // The per-chunk CTA counters compare against epoch * gridDim.x, so the grid depends on nothing but
     // the device: one full wave (CTAs without work just count).

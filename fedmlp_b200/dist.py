@@ -170,8 +170,8 @@ class QueuedAggregation:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         lib = cabi.lib()
         n = int(lib.fmlp_fedavg_allreduce_q_buffer_floats(self.P, self.T, self.M))
-        if n_chunks is None:
-            n_chunks = int(os.environ.get("FMLP_ARQ_CHUNKS", "4"))
+        if n_chunks is None:     # r02 sweeps (profiles/r02_arq_sweep_*gpu.jsonl): 4 chunks at 2 GPUs, 8 at 8
+            n_chunks = int(os.environ.get("FMLP_ARQ_CHUNKS", "8" if self.world >= 4 else "4"))
         self.n_chunks = max(1, min(16, int(n_chunks)))
         self.max_ctas = int(os.environ.get("FMLP_ARQ_CTAS", "0")) if max_ctas is None else int(max_ctas)
         self.fold_iters, self.red_iters = int(fold_iters), int(red_iters)
