@@ -70,6 +70,7 @@ SIGNATURES = {
     "fmlp_loss_stage1_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _u32, _u32, _i, _p, _p, _p, _p, _sz, _p]),
     "fmlp_loss_stage2_f32": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _p]),
     "fmlp_loss_stage2_seg_f32": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "fmlp_fill_loss_stage2_f32": (_i, [_p, _p, _i64, _p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "fmlp_adam_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i64, _i, _p]),
     "fmlp_scale_f32": (_i, [_p, _i64, _p, _p]),
 }

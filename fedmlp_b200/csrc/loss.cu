@@ -9,9 +9,10 @@
 //   backward  dBCE/dp  = g*(p-y) / max((1-p)*p, 1e-12)         (binary_cross_entropy_backward)
 //             dMSE/dp  = (2*(p-t))*g                             (mse_loss_backward, reduction none)
 //             dp/dz    = (g*(1-p))*p                             (sigmoid_backward)
-// The kernels are launched cooperatively: phase boundaries (stage-2 denominator, final loss
-// reduction) are grid barriers, per-CTA partials are combined in CTA order -> deterministic,
-// no atomics, no pre-zeroed workspace.
+// The stand-alone loss kernels are launched cooperatively: phase boundaries (stage-2 denominator, final
+// loss reduction) are grid barriers, per-CTA partials are combined in CTA order -> deterministic, no
+// atomics, no pre-zeroed workspace.  The batched round uses fill_loss_stage2_kernel below (round 2): mask
+// fill fused in, ordinary launch, last-arriving CTA does the final reduction.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -261,6 +262,143 @@ __global__ void __launch_bounds__(kLossThreads) loss_stage2_kernel(const __grid_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Round 2: label / mask fill (DatasetSplit_pseudo.__getitem__, utils/local_training.py:1456-1477, :1173)
+// FUSED into the stage-2 loss (:1171-1188), as an ordinary (non-cooperative) launch.
+//   * y / distill_cls / sup_cls are computed on the fly from the true labels and the tag state the select
+//     kernel just updated, and written out as by-products (the training loop and the tests still read them):
+//     one pass over [N, C] instead of two, one launch instead of two;
+//   * the denominators come from the select kernel's per-(client, class) candidate counts, so no counting
+//     phase and no grid barrier in front of the gradient;
+//   * the final per-client reduction is done by whichever CTA finishes LAST (a counter in the workspace,
+//     reset by that CTA), not behind a cooperative grid.sync(): the launch needs no co-residency, so it
+//     overlaps the kernels of the other streams, and it is chained to the select kernel by a programmatic
+//     dependent launch.  Partials are still combined in CTA order -> deterministic.
+struct FillLossArgs {
+    const float *z, *zg, *labels;
+    const uint8_t* tag;
+    float *y, *distill, *sup;          // by-products, any may be null
+    float *loss, *dz;                  // loss[S]
+    float* ws;                         // [0,G) sup partials, [G,2G) dis partials, word 3G = arrival counter (zero at first use)
+    const int32_t* seg_class_distill;  // [S][C] rows with tag == 0 per (client, class) = distilled entries of missing classes
+    int64_t ld_tag;
+    int64_t el_per_cta;
+    int C;
+    int variant;
+    SegTable seg;                      // mask_a = active classes, mask_b = missing classes
+};
+
+__global__ void __launch_bounds__(kLossThreads) fill_loss_stage2_kernel(const __grid_constant__ FillLossArgs a) {
+    __shared__ float s_red[32];
+    __shared__ int s_redi[32];
+    __shared__ float s_den[2];
+    __shared__ int s_last;
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // tag state / counts of the select kernel
+    const int S = a.seg.S;
+    const int64_t n_el = a.seg.rows[S] * a.C;
+    const int64_t e_begin = (int64_t)blockIdx.x * a.el_per_cta;
+    const int64_t e_end = min(n_el, e_begin + a.el_per_cta);
+    const int s_first = e_begin < n_el ? find_segment(a.seg.rows, S, e_begin / a.C) : S;
+
+    for (int s = s_first; s < S; ++s) {
+        const int64_t seg_lo = a.seg.rows[s] * a.C, seg_hi = a.seg.rows[s + 1] * a.C;
+        const int64_t lo = max(e_begin, seg_lo), hi = min(e_end, seg_hi);
+        if (lo >= e_end) break;
+        if (hi <= lo) continue;  // empty segment
+        int td = 0;
+        if (threadIdx.x < a.C && ((a.seg.mask_b[s] >> threadIdx.x) & 1u)) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
+        td = block_sum_i(td, s_redi);
+        if (threadIdx.x == 0) {
+            const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
+            // :1188  sup_cls.sum()          :1187  sup_cls.sum() + distill_cls.sum()
+            s_den[0] = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+        }
+        __syncthreads();
+        const float den = s_den[0];
+        const float g = __fdiv_rn(1.f, den);  // d loss / d numerator
+        const uint32_t act = a.seg.mask_a[s], mis = a.seg.mask_b[s];
+        float num_sup = 0.f, num_dis = 0.f;
+        for (int64_t base = lo + threadIdx.x; base < hi; base += (int64_t)kLossThreads * kLossUnroll) {
+            float vz[kLossUnroll], vg[kLossUnroll], vy[kLossUnroll], vd[kLossUnroll];
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int64_t e = base + (int64_t)u * kLossThreads;
+                const bool ok = e < hi;
+                vz[u] = ok ? a.z[e] : 0.f;
+                vg[u] = (ok && a.variant == FMLP_LOSS2_SUP_DIS) ? a.zg[e] : 0.f;
+                float y = 0.f, dis = 0.f;
+                if (ok) {
+                    const int64_t row = e / a.C;
+                    const int c = (int)(e - row * a.C);
+                    if ((act >> c) & 1u) {
+                        y = a.labels[e];                              // annotated class keeps its label (:1458-1460)
+                    } else if ((mis >> c) & 1u) {
+                        const uint8_t t = a.tag[(int64_t)c * a.ld_tag + row];
+                        y = (t == 2) ? 1.f : 0.f;                     // in the noise list -> pseudo-positive (:1464-1466)
+                        dis = (t == 0) ? 1.f : 0.f;                   // in neither list -> distilled (:1467-1468)
+                    }
+                    if (a.y) a.y[e] = y;
+                    if (a.distill) a.distill[e] = dis;
+                    if (a.sup) a.sup[e] = 1.f - dis;                  // sup_cls = ~distill_cls (:1173)
+                }
+                vy[u] = y; vd[u] = dis;
+            }
+#pragma unroll
+            for (int u = 0; u < kLossUnroll; ++u) {
+                const int64_t e = base + (int64_t)u * kLossThreads;
+                if (e >= hi) continue;
+                const float p = sigmoid_ref(vz[u]);
+                const float dist = vd[u];
+                const float sup = (dist != 0.f) ? 0.f : 1.f;
+                num_sup += __fmul_rn(bce_fwd(p, vy[u]), sup);
+                float gp = bce_bwd(__fmul_rn(g, sup), p, vy[u]);
+                if (a.variant == FMLP_LOSS2_SUP_DIS) {
+                    const float pg = sigmoid_ref(vg[u]);
+                    const float d = __fsub_rn(p, pg);
+                    num_dis += __fmul_rn(__fmul_rn(d, d), dist);
+                    gp = __fadd_rn(gp, mse_bwd(__fmul_rn(g, dist), p, pg));
+                }
+                a.dz[e] = sigmoid_bwd(gp, p);
+            }
+        }
+        const float bn_sup = block_sum(num_sup, s_red);
+        const float bn_dis = block_sum(num_dis, s_red);
+        if (threadIdx.x == 0) { a.ws[blockIdx.x + s] = bn_sup; a.ws[kLossMaxGrid + blockIdx.x + s] = bn_dis; }
+        __syncthreads();  // s_den reuse
+    }
+    // ---- the CTA that arrives last adds every client's partials in CTA order ----------------------
+    unsigned int* counter = reinterpret_cast<unsigned int*>(a.ws + 3 * kLossMaxGrid);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) + 1u == gridDim.x) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int s = 0; s < S; ++s) {
+        const int64_t seg_lo = a.seg.rows[s] * a.C, seg_hi = a.seg.rows[s + 1] * a.C;
+        float ts = 0.f, tdis = 0.f;
+        int td = 0;
+        if (seg_hi > seg_lo) {
+            const int b0 = (int)(seg_lo / a.el_per_cta), b1 = (int)((seg_hi - 1) / a.el_per_cta);
+            for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) {
+                ts += __ldcg(a.ws + b + s); tdis += __ldcg(a.ws + kLossMaxGrid + b + s);
+            }
+            if (threadIdx.x < a.C && ((a.seg.mask_b[s] >> threadIdx.x) & 1u)) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
+        }
+        ts = block_sum(ts, s_red);
+        tdis = block_sum(tdis, s_red);
+        td = block_sum_i(td, s_redi);
+        if (threadIdx.x == 0) {
+            const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
+            const float den = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+            const float num = a.variant == FMLP_LOSS2_SUP ? ts : __fadd_rn(ts, tdis);
+            a.loss[s] = __fdiv_rn(num, den);
+        }
+    }
+    if (threadIdx.x == 0) *counter = 0u;     // ready for the next launch (stream order makes it visible)
+}
+
 __global__ void scale_kernel(float* x, int64_t n, const float* scale) {
     const float s = *scale;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -364,6 +502,45 @@ extern "C" int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const f
                                         const int32_t* seg_class_distill, float* loss, float* dz, void* ws,
                                         size_t ws_bytes, fmlp_stream_t stream) {
     return launch_loss2(z, zg, y, distill, C, S, seg_rows, variant, seg_class_distill, loss, dz, ws, ws_bytes, stream);
+}
+
+extern "C" int fmlp_fill_loss_stage2_f32(const float* labels, const uint8_t* tag, int64_t ld_tag, const float* z,
+                                         const float* zg, int C, int S, const int64_t* seg_rows,
+                                         const uint32_t* seg_active, const uint32_t* seg_missing, int variant,
+                                         const int32_t* seg_class_distill, float* y, float* distill, float* sup,
+                                         float* loss, float* dz, void* ws, size_t ws_bytes, fmlp_stream_t stream) {
+    if (!labels || !tag || !z || !seg_active || !seg_missing || !seg_class_distill || !loss || !dz || !ws || C < 1 ||
+        C > FMLP_MAX_CLASSES)
+        return FMLP_ERR_BAD_ARG;
+    if (variant != FMLP_LOSS2_SUP && variant != FMLP_LOSS2_SUP_DIS) return FMLP_ERR_BAD_ARG;
+    if (variant == FMLP_LOSS2_SUP_DIS && !zg) return FMLP_ERR_BAD_ARG;
+    if (ws_bytes < fmlp_loss_ws_bytes(0, C)) return FMLP_ERR_WORKSPACE;
+    FillLossArgs a;
+    int rc = fill_seg_table(a.seg, S, seg_rows, seg_active, seg_missing);
+    if (rc != FMLP_OK) return rc;
+    if (ld_tag < seg_rows[S]) return FMLP_ERR_BAD_ARG;
+    a.z = z; a.zg = zg; a.labels = labels; a.tag = tag; a.y = y; a.distill = distill; a.sup = sup; a.loss = loss; a.dz = dz;
+    a.ws = (float*)ws; a.seg_class_distill = seg_class_distill; a.ld_tag = ld_tag; a.C = C; a.variant = variant;
+    const int64_t n_el = seg_rows[S] * C;
+    const int sms = sm_count();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    const int64_t tile = (int64_t)kLossThreads * kLossUnroll;
+    int64_t grid = (n_el + tile - 1) / tile;
+    if (grid > 2 * (int64_t)sms) grid = 2 * (int64_t)sms;        // two CTAs per SM: latency-bound element-wise work
+    if (grid > kLossMaxGrid - FMLP_MAX_SEGMENTS) grid = kLossMaxGrid - FMLP_MAX_SEGMENTS;  // slots b + s
+    if (grid < 1) grid = 1;
+    int64_t epc = (n_el + grid - 1) / grid;
+    epc = (epc + tile - 1) / tile * tile;
+    if (epc < tile) epc = tile;
+    a.el_per_cta = epc;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kLossThreads); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fill_loss_stage2_kernel, a);
+    return e == cudaSuccess ? launch_status() : (int)e;
 }
 
 extern "C" int fmlp_scale_f32(float* x, int64_t n, const float* scale_dev, fmlp_stream_t stream) {

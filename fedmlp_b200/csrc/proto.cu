@@ -41,6 +41,7 @@ constexpr int kProtoCountStride = 2 * kProtoMaxActive + FMLP_MAX_CLASSES;
 
 template <int NA>
 __global__ void __launch_bounds__(512, NA == 1 ? 2 : 1) proto_accum_kernel(const __grid_constant__ ProtoArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finalize kernel is a programmatic dependent launch
     __shared__ int s_t[FMLP_MAX_CLASSES];
     const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     const bool col_ok = col < a.D;
@@ -170,6 +171,7 @@ struct ProtoFinArgs {
 // the L2 round trips overlap instead of forming one 70-deep dependent chain (r01 ncu: 33 us).
 // Then the row is divided by its count (tensor / python int -> fp32 divide, :997-999,1241-1248).
 __global__ void __launch_bounds__(256) proto_finalize_kernel(const __grid_constant__ ProtoFinArgs a) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // slot partials of the accumulate kernel
     __shared__ int s_n[8];
     __shared__ float4 s_part[4][64];
     const int s = blockIdx.x / (2 * a.C);
@@ -357,8 +359,16 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
         if (rc != FMLP_OK) return rc;
         f.D = D; f.C = C; f.NA = NA; f.guard_empty = guard_empty; f.first_pass = first ? 1 : 0; f.has_t = a.do_t;
         dim3 fgrid((unsigned)(S * 2 * C), (unsigned)((D + 255) / 256));
-        proto_finalize_kernel<<<fgrid, 256, 0, st>>>(f);
-        rc = launch_status();
+        {
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cfg.gridDim = fgrid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, proto_finalize_kernel, f);
+            rc = e == cudaSuccess ? launch_status() : (int)e;
+        }
         if (rc != FMLP_OK) return rc;
         first = false;
         bool more = false;

@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
     __shared__ int s_found[2][3];            // per side: bin, remaining-in-bin, bin count
     __shared__ int s_count[3];               // selected per side, candidates seen
 
+    // chained to the similarity kernel (and the fill+loss kernel to this one) by programmatic dependent launches:
+    // the launch latency of each hides behind its predecessor; the data dependency is the wait below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int item = blockIdx.x;
     const int s = item / a.C, c = item - s * a.C;
     int32_t* counts = a.counts + (int64_t)item * 4;
@@ -346,10 +350,17 @@ extern "C" int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, i
     for (int s = 0; s < S; ++s) max_rows = std::max<int64_t>(max_rows, seg_rows[s + 1] - seg_rows[s]);
     const unsigned grid = (unsigned)(S * C);
     cudaStream_t st = (cudaStream_t)stream;
-    if (max_rows <= 8 * 1024) tag_select_kernel<8, 1024><<<grid, 1024, 0, st>>>(a);
-    else if (max_rows <= 16 * 1024) tag_select_kernel<16, 1024><<<grid, 1024, 0, st>>>(a);
-    else tag_select_kernel<0, 1024><<<grid, 1024, 0, st>>>(a);
-    return launch_status();
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaError_t e;
+    if (max_rows <= 8 * 1024) e = cudaLaunchKernelEx(&cfg, tag_select_kernel<8, 1024>, a);
+    else if (max_rows <= 16 * 1024) e = cudaLaunchKernelEx(&cfg, tag_select_kernel<16, 1024>, a);
+    else e = cudaLaunchKernelEx(&cfg, tag_select_kernel<0, 1024>, a);
+    return e == cudaSuccess ? launch_status() : (int)e;
 }
 
 extern "C" int fmlp_mask_fill(const float* labels_in, const uint8_t* tag, int64_t ld_tag, int C, int S,

@@ -177,6 +177,8 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // the selection kernel behind this one is a programmatic dependent launch too: let it be set up now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int64_t n_tiles = (a.n_total + ROWS - 1) / ROWS;
     const int my_groups = (NG > warp) ? (NG - warp + W - 1) / W : 0;       // column groups warp, warp+W, ...

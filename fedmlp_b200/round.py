@@ -77,7 +77,7 @@ class _Plan:
         with torch.cuda.device(dev):
             self.ws_sim = torch.empty(max(lib.fmlp_tag_sim_ws_bytes(C, D), 256), dtype=torch.uint8, device=dev)
             self.ws_select = torch.empty(max(lib.fmlp_tag_select_ws_bytes(S, C, self.cap), 256), dtype=torch.uint8, device=dev)
-            self.ws_loss = torch.empty(max(lib.fmlp_loss_ws_bytes(N, C), 256), dtype=torch.uint8, device=dev)
+            self.ws_loss = torch.zeros(max(lib.fmlp_loss_ws_bytes(N, C), 256), dtype=torch.uint8, device=dev)   # arrival counter starts at 0
             self.ws_proto = torch.empty(max(lib.fmlp_proto_ws_bytes(N, D, C, S), 256), dtype=torch.uint8, device=dev)
         self.rows = cabi.i64_array(shard.seg_rows)
         self.active = cabi.u32_array([cabi.class_mask(a) for a in shard.active])
@@ -248,14 +248,14 @@ class ClientShard:
                                           pl.rows, pl.missing, self.clean_frac, self.noise_frac, pl.counts.data_ptr(),
                                           pl.remaining.data_ptr(), pl.sel.data_ptr(), pl.cap, pl.ws_select.data_ptr(),
                                           pl.ws_select.numel(), st), "fmlp_tag_select")
-                check(lib.fmlp_mask_fill(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], C, S, pl.rows, pl.active,
-                                         pl.missing, pl.y.data_ptr(), pl.distill.data_ptr(), pl.sup.data_ptr(), st),
-                      "fmlp_mask_fill")
                 mark("select_fill")
-                check(lib.fmlp_loss_stage2_seg_f32(logits.data_ptr(), logits_glob.data_ptr(), pl.y.data_ptr(),
-                                                   pl.distill.data_ptr(), C, S, pl.rows, self.loss_variant,
-                                                   pl.remaining.data_ptr(), pl.losses.data_ptr(), pl.dz.data_ptr(),
-                                                   pl.ws_loss.data_ptr(), pl.ws_loss.numel(), st), "fmlp_loss_stage2_seg_f32")
+                # label / mask fill fused into the loss: one ordinary launch behind the selection (round 2)
+                check(lib.fmlp_fill_loss_stage2_f32(labels.data_ptr(), tg.tag.data_ptr(), tg.tag.shape[1], logits.data_ptr(),
+                                                    logits_glob.data_ptr(), C, S, pl.rows, pl.active, pl.missing,
+                                                    self.loss_variant, pl.remaining.data_ptr(), pl.y.data_ptr(),
+                                                    pl.distill.data_ptr(), pl.sup.data_ptr(), pl.losses.data_ptr(),
+                                                    pl.dz.data_ptr(), pl.ws_loss.data_ptr(), pl.ws_loss.numel(), st),
+                      "fmlp_fill_loss_stage2_f32")
                 mark("loss")
 
             if timers == "external":

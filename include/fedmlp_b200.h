@@ -335,6 +335,17 @@ int fmlp_loss_stage2_seg_f32(const float* z, const float* zg, const float* y, co
                              const int32_t* seg_class_distill, float* loss, float* dz, void* ws,
                              size_t ws_bytes, fmlp_stream_t stream);
 
+/* Label / mask fill fused into the segmented stage-2 loss (utils/local_training.py:1456-1477 + :1171-1188) in ONE
+ * ordinary launch: y / distill / sup (any may be NULL) are written as by-products, the denominators come from
+ * `seg_class_distill` = fmlp_tag_select's `remaining` counts [S][C], the per-client losses are reduced by the CTA
+ * that finishes last.  `ws`: fmlp_loss_ws_bytes bytes that were ZERO when first used (the kernel leaves its
+ * arrival counter zero); chained to the preceding fmlp_tag_select by a programmatic dependent launch.       */
+int fmlp_fill_loss_stage2_f32(const float* labels, const uint8_t* tag, int64_t ld_tag, const float* z,
+                              const float* zg, int C, int S, const int64_t* seg_rows,
+                              const uint32_t* seg_active, const uint32_t* seg_missing, int variant,
+                              const int32_t* seg_class_distill, float* y, float* distill, float* sup,
+                              float* loss, float* dz, void* ws, size_t ws_bytes, fmlp_stream_t stream);
+
 /* ------------------------------------------------------------------ fused Adam
  * One torch.optim.Adam step (amsgrad=False; the optimizer the reference re-creates every round,
  * utils/local_training.py:912,1149) over the PARAMETER runs of flat fp32 buffers p/g/m/v that

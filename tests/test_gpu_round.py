@@ -54,6 +54,10 @@ def test_round_hot_path_matches_per_client_oracle(lib, mode):
             tgt, dis = O.mask_fill(labels[r0:r1].numpy(), list(range(n)), active[s], shard.missing[s], states[s].traindata_idx)
             ref_loss, rdz = O.loss_and_grads(lambda z, g_, y, d: O.stage2_loss(z, g_, y, d), logits[r0:r1], zg[r0:r1],
                                              torch.from_numpy(tgt), torch.from_numpy(dis), n_grad=1)
+            # by-products of the fused fill + loss kernel (DatasetSplit_pseudo :1456-1477, sup_cls :1173)
+            np.testing.assert_array_equal(shard._plan.y[r0:r1].cpu().numpy(), tgt)
+            np.testing.assert_array_equal(shard._plan.distill[r0:r1].cpu().numpy(), dis)
+            np.testing.assert_array_equal(shard._plan.sup[r0:r1].cpu().numpy(), 1.0 - dis)
             assert abs(float(res.losses[s]) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
             np.testing.assert_allclose(res.dz[r0:r1].cpu().numpy(), rdz.numpy(), rtol=1e-5, atol=1e-6 * float(rdz.abs().max()))
             ref_p, ref_n, ref_t = O.prototype_build(feat2[r0:r1], labels[r0:r1], logits2[r0:r1], active[s], shard.missing[s],
