@@ -858,6 +858,7 @@ def measure_api(w: Workload, dev, reps=10):
     out = {"fedavg_state_dicts_ms": wall(lambda: F.FedAvg(gpu_sds, dict_len)),
            "fedavg_flat_state_dicts_ms": wall(lambda: F.FedAvg(flat_sds, dict_len)),
            "fedavg_cpu_state_dicts_ms": wall(lambda: F.FedAvg(cpu_sds, dict_len)),
+           "fedavg_flat_buffers_ms": wall(lambda: F.fedavg_flat_buffers([f.flat_f32 for f in flat_sds], dict_len)),
            "tensors_per_state_dict": len(shapes), "clients": K}
     n, C, D = w.n, w.C, w.D
     g = torch.Generator(device=dev).manual_seed(3)
@@ -866,7 +867,7 @@ def measure_api(w: Workload, dev, reps=10):
     tb = F.TagBatch([0, n], C, [[0]], [list(range(1, C))], device=dev)
     out["train_FedMLP_tag_ms"] = wall(lambda: tb.step(feat, proto, 0.005, 0.01, mode="folded"))
     out["note"] = ("wall clock incl. Python + a device sync; scattered dicts: one pointer-table pass over 727 x K tensors per call "
-                   "(table re-uploaded only when a pointer changed); CPU dicts: pinned staging (pooled) + H2D + D2H of the result")
+                   "(table re-uploaded only when a pointer changed) + a 727-entry result dict; flat state_dicts: K pointers + the result dict; flat buffers: K pointers, one [P] tensor out; CPU dicts: pinned staging (pooled) + H2D + D2H of the result")
     return out
 
 

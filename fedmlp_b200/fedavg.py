@@ -66,8 +66,13 @@ def _multi_plan(layout: FlatLayout, device):
 
 
 def _check_same_keys(w):
-    keys = list(w[0].keys())
+    lay0 = getattr(w[0], "layout", None)
+    keys = None
     for i in range(1, len(w)):
+        if lay0 is not None and getattr(w[i], "layout", None) is lay0:
+            continue        # FlatStateDicts of one layout: same keys by construction
+        if keys is None:
+            keys = list(w[0].keys())
         if list(w[i].keys()) != keys:
             raise KeyError(f"FedAvg: client {i} has different state_dict keys than client 0")
 
@@ -136,7 +141,7 @@ def _fedavg_cuda(w, dict_len, divide=True):
     integral = all(_is_integral(x) for x in dict_len)
     divisor = sum(dict_len) if divide else 1.0
     div_flag = cabi.FEDAVG_DIVIDE if divide else 0
-    out = FlatStateDict.empty(layout, dev, ints_as_float=True)
+    out = FlatStateDict.empty(layout, dev, ints_as_float=True, lazy=True)
     lib = cabi.lib()
     with torch.cuda.device(dev):
         st = cabi.stream_ptr(dev)

@@ -40,6 +40,9 @@ _layout_cache: dict = {}
 
 
 def layout_of(state_dict) -> FlatLayout:
+    lay = getattr(state_dict, "layout", None)
+    if isinstance(lay, FlatLayout) and not getattr(state_dict, "ints_as_float", False):
+        return lay          # a FlatStateDict knows its layout (its keys / shapes cannot change)
     sig = tuple((k, tuple(v.shape), v.dtype) for k, v in state_dict.items())
     lay = _layout_cache.get(sig)
     if lay is not None:
@@ -72,16 +75,31 @@ class FlatStateDict(OrderedDict):
     flat_i64: torch.Tensor | None
 
     @classmethod
-    def empty(cls, layout: FlatLayout, device, ints_as_float: bool = False):
+    def empty(cls, layout: FlatLayout, device, ints_as_float: bool = False, lazy: bool = False, zero: bool = True):
         """ints_as_float: int64 entries are float32 (FedAvg's output dtype quirk) stored behind
-        the fp32 parameters in the same buffer."""
+        the fp32 parameters in the same buffer.
+        lazy: the 727 views of a DenseNet121 cost milliseconds of Python to create; a lazy dict allocates only
+        the flat buffers and builds its entries on first access as a mapping (FedAvg outputs: the flat round
+        loop never looks at them, load_state_dict does).  zero=False skips the memset (every element that a
+        view can see is about to be written)."""
         self = cls()
         self.layout = layout
         extra = layout.n_i64 if ints_as_float else 0
-        self.flat_f32 = torch.zeros(layout.n_f32 + extra, dtype=torch.float32, device=device)
-        self.flat_i64 = None if ints_as_float or layout.n_i64 == 0 else torch.zeros(
+        alloc = torch.zeros if zero else torch.empty
+        self.flat_f32 = alloc(layout.n_f32 + extra, dtype=torch.float32, device=device)
+        self.flat_i64 = None if ints_as_float or layout.n_i64 == 0 else alloc(
             layout.n_i64, dtype=torch.int64, device=device)
         self.ints_as_float = ints_as_float
+        self._pending = True
+        if not lazy:
+            self._materialise()
+        return self
+
+    def _materialise(self):
+        if not getattr(self, "_pending", False):
+            return
+        self._pending = False
+        layout, ints_as_float = self.layout, self.ints_as_float
         for i, k in enumerate(layout.keys):
             n, off = layout.numels[i], layout.offsets[i]
             if not layout.is_int[i]:
@@ -91,7 +109,57 @@ class FlatStateDict(OrderedDict):
             else:
                 v = self.flat_i64[off:off + n]
             OrderedDict.__setitem__(self, k, v.view(layout.shapes[i]))
-        return self
+
+    # every way of looking at the mapping goes through _materialise (overriding __iter__ also keeps
+    # dict(x) / OrderedDict(x) / update(x) off CPython's storage-level fast path)
+    def __getitem__(self, key):
+        self._materialise()
+        return OrderedDict.__getitem__(self, key)
+
+    def __iter__(self):
+        self._materialise()
+        return OrderedDict.__iter__(self)
+
+    def __len__(self):
+        return len(self.layout.keys) if hasattr(self, "layout") else OrderedDict.__len__(self)
+
+    def __contains__(self, key):
+        self._materialise()
+        return OrderedDict.__contains__(self, key)
+
+    def keys(self):
+        self._materialise()
+        return OrderedDict.keys(self)
+
+    def values(self):
+        self._materialise()
+        return OrderedDict.values(self)
+
+    def items(self):
+        self._materialise()
+        return OrderedDict.items(self)
+
+    def get(self, key, default=None):
+        self._materialise()
+        return OrderedDict.get(self, key, default)
+
+    def __reversed__(self):
+        self._materialise()
+        return OrderedDict.__reversed__(self)
+
+    def __eq__(self, other):
+        self._materialise()
+        return OrderedDict.__eq__(self, other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._materialise()
+        return OrderedDict.__repr__(self)
+
+    def copy(self):
+        self._materialise()
+        return OrderedDict(self.items())
 
     @classmethod
     def from_state_dict(cls, state_dict, device=None):
@@ -106,7 +174,8 @@ class FlatStateDict(OrderedDict):
     def __setitem__(self, key, value):
         """Assigning to an existing key copies INTO the flat view (the dict keeps aliasing its buffers, which is
         what FedAvg's flat path reads); a new key would break the layout and is refused."""
-        if key in self and isinstance(value, torch.Tensor):
+        self._materialise()
+        if OrderedDict.__contains__(self, key) and isinstance(value, torch.Tensor):
             OrderedDict.__getitem__(self, key).copy_(value)
             return
         raise KeyError(f"FlatStateDict has a fixed layout; cannot add key {key!r}")
