@@ -282,9 +282,21 @@ __global__ void __launch_bounds__(256) proto_avg_kernel(const __grid_constant__ 
     const int64_t client_stride = (int64_t)a.rpc * a.C * a.D;
     for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
         float acc = 0.f;
-        for (int i = 0; i < a.K; ++i)
-            if ((members >> i) & 1ull)
-                acc = __fadd_rn(__fmul_rn(a.protos[i * client_stride + row_off + d], a.w[i]), acc);
+        // the members' values are loaded eight at a time before they are folded (in client order): the fold is
+        // a dependent chain, the loads need not be (r02 ncu: 7.2 us for 10 x 1024 outputs with one load per step)
+        for (int i0 = 0; i0 < a.K; i0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u;
+                v[u] = (i < a.K && ((members >> i) & 1ull)) ? a.protos[i * client_stride + row_off + d] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u;
+                if (i < a.K && ((members >> i) & 1ull)) acc = __fadd_rn(__fmul_rn(v[u], a.w[i]), acc);
+            }
+        }
         a.out[row_off + d] = __fdiv_rn(acc, divisor);
     }
 }

@@ -404,9 +404,18 @@ __global__ void __launch_bounds__(256) agg_tail_pack_kernel(const int32_t* __res
     } else if (i < 2 * C) {
         const int c = i - C;
         double s = 0.0;
-        // t_k[c] = count / N_k as numpy float64 (local_training.py:1000,1249), times the client weight
-        for (int k = 0; k < a.S; ++k)
-            if ((a.neg[k] >> c) & 1u) s += ((double)(tcnt ? tcnt[k * C + c] : 0) / (double)a.rows[k]) * a.w[k];
+        // t_k[c] = count / N_k as numpy float64 (local_training.py:1000,1249), times the client weight; the
+        // counts are loaded eight clients at a time (independent loads), the sum stays in client order
+        for (int k0 = 0; k0 < a.S; k0 += 8) {
+            int cnt[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cnt[u] = (tcnt && k0 + u < a.S) ? tcnt[(k0 + u) * C + c] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                if (k < a.S && ((a.neg[k] >> c) & 1u)) s += ((double)cnt[u] / (double)a.rows[k]) * a.w[k];
+            }
+        }
         out[i] = s;
     } else if (i < 3 * C) {
         const int c = i - 2 * C;
@@ -416,7 +425,13 @@ __global__ void __launch_bounds__(256) agg_tail_pack_kernel(const int32_t* __res
     } else if (i < 3 * C + a.J) {
         const int j = i - 3 * C;
         double s = 0.0;
-        for (int k = 0; k < a.S; ++k) s += (double)a.counters[k][j] * a.w[k];
+        for (int k0 = 0; k0 < a.S; k0 += 8) {
+            long long v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < a.S) ? a.counters[k0 + u][j] : 0ll;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (k0 + u < a.S) s += (double)v[u] * a.w[k0 + u];
+        }
         out[i] = s;
     }
 }

@@ -290,7 +290,6 @@ struct FillLossArgs {
 
 __global__ void __launch_bounds__(kLossThreads) fill_loss_stage2_kernel(const __grid_constant__ FillLossArgs a) {
     __shared__ float s_red[32];
-    __shared__ int s_redi[32];
     __shared__ float s_den[2];
     __shared__ int s_last;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // tag state / counts of the select kernel
@@ -305,13 +304,15 @@ __global__ void __launch_bounds__(kLossThreads) fill_loss_stage2_kernel(const __
         const int64_t lo = max(e_begin, seg_lo), hi = min(e_end, seg_hi);
         if (lo >= e_end) break;
         if (hi <= lo) continue;  // empty segment
-        int td = 0;
-        if (threadIdx.x < a.C && ((a.seg.mask_b[s] >> threadIdx.x) & 1u)) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
-        td = block_sum_i(td, s_redi);
-        if (threadIdx.x == 0) {
-            const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
-            // :1188  sup_cls.sum()          :1187  sup_cls.sum() + distill_cls.sum()
-            s_den[0] = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+        if (threadIdx.x < 32) {      // C <= 32: one warp adds the client's per-class counts
+            int td = 0;
+            if (threadIdx.x < a.C && ((a.seg.mask_b[s] >> threadIdx.x) & 1u)) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
+            td = warp_sum_i(td);
+            if (threadIdx.x == 0) {
+                const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
+                // :1188  sup_cls.sum()          :1187  sup_cls.sum() + distill_cls.sum()
+                s_den[0] = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
+            }
         }
         __syncthreads();
         const float den = s_den[0];
@@ -375,21 +376,24 @@ __global__ void __launch_bounds__(kLossThreads) fill_loss_stage2_kernel(const __
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int s = 0; s < S; ++s) {
+    // one warp per client: lane-strided sums over the client's CTA slots, then a shuffle tree (a fixed order for
+    // a given launch geometry -> deterministic); no block-wide barriers on the tail of the kernel
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = warp; s < S; s += kLossThreads / 32) {
         const int64_t seg_lo = a.seg.rows[s] * a.C, seg_hi = a.seg.rows[s + 1] * a.C;
         float ts = 0.f, tdis = 0.f;
         int td = 0;
         if (seg_hi > seg_lo) {
             const int b0 = (int)(seg_lo / a.el_per_cta), b1 = (int)((seg_hi - 1) / a.el_per_cta);
-            for (int b = b0 + threadIdx.x; b <= b1; b += kLossThreads) {
+            for (int b = b0 + lane; b <= b1; b += 32) {
                 ts += __ldcg(a.ws + b + s); tdis += __ldcg(a.ws + kLossMaxGrid + b + s);
             }
-            if (threadIdx.x < a.C && ((a.seg.mask_b[s] >> threadIdx.x) & 1u)) td = a.seg_class_distill[(int64_t)s * a.C + threadIdx.x];
+            if (lane < a.C && ((a.seg.mask_b[s] >> lane) & 1u)) td = a.seg_class_distill[(int64_t)s * a.C + lane];
         }
-        ts = block_sum(ts, s_red);
-        tdis = block_sum(tdis, s_red);
-        td = block_sum_i(td, s_redi);
-        if (threadIdx.x == 0) {
+        ts = warp_sum(ts);
+        tdis = warp_sum(tdis);
+        td = warp_sum_i(td);
+        if (lane == 0) {
             const float sum_dis = (float)td, sum_sup = (float)((seg_hi - seg_lo) - td);
             const float den = a.variant == FMLP_LOSS2_SUP ? sum_sup : __fadd_rn(sum_sup, sum_dis);
             const float num = a.variant == FMLP_LOSS2_SUP ? ts : __fadd_rn(ts, tdis);
