@@ -51,6 +51,7 @@ SIGNATURES = {
     "fmlp_agg_tail_pack_f64": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fmlp_agg_finalize_f32": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _p, _p]),
     "fmlp_proto_avg_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fmlp_agg_tails_local_f32": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _d, _p, _p, _p]),
     "fmlp_tao_avg_f64": (_i, [_p, _i, _i, _p, _p, _d, _p, _p]),
     "fmlp_model_dist_ws_bytes": (_sz, [_i64, _i]),
     "fmlp_model_dist_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _sz, _p]),

@@ -273,8 +273,7 @@ struct ProtoAvgArgs {
 // client) order starting from zeros, then / np.sum(weights[act]).  The divisor is formed by
 // the host (entry point below) from the original weights in double and rounded once to fp32,
 // which is what torch does with a numpy scalar divisor.
-__global__ void __launch_bounds__(256) proto_avg_kernel(const __grid_constant__ ProtoAvgArgs a) {
-    const int row = blockIdx.x;
+__device__ __forceinline__ void proto_avg_row(const ProtoAvgArgs& a, int row) {
     const int c = row / a.rpc;
     const uint64_t members = a.class_clients[c];
     const float divisor = a.class_div[c];
@@ -298,6 +297,67 @@ __global__ void __launch_bounds__(256) proto_avg_kernel(const __grid_constant__ 
             }
         }
         a.out[row_off + d] = __fdiv_rn(acc, divisor);
+    }
+}
+
+__global__ void __launch_bounds__(256) proto_avg_kernel(const __grid_constant__ ProtoAvgArgs a) { proto_avg_row(a, blockIdx.x); }
+
+// ---- all the small tails of the single-GPU aggregation in ONE launch (main.py:218-234) --------
+// CTAs [0, 2C): FedAvg_proto rows (bit-exact, as above).  CTA 2C: FedAvg_tao (utils/FedAvg.py:51-70, IEEE
+// double in the reference's order, t_k[c] = count / N_k as at local_training.py:1000,1249) and the int64
+// BatchNorm counters (FedAvg.py:9-13: weighted sum, then the float32 divide).  Round 1/early round 2 ran
+// these as three dependent launches (proto_avg -> tail pack -> finalize, 16 us of launch latency at the
+// end of the aggregation chain).
+struct AggTailsArgs {
+    ProtoAvgArgs p;
+    double w[FMLP_MAX_CLIENTS];
+    int64_t rows[FMLP_MAX_CLIENTS];
+    uint32_t neg[FMLP_MAX_CLIENTS];
+    const int64_t* counters[FMLP_MAX_CLIENTS];
+    const int32_t* tcnt;   // [K][C]
+    double* tao_out;       // [C]
+    float* counters_out;   // [J]
+    double total;
+    int J;
+};
+
+__global__ void __launch_bounds__(256) agg_tails_local_kernel(const __grid_constant__ AggTailsArgs a) {
+    const int n_rows = a.p.rpc * a.p.C;
+    if ((int)blockIdx.x < n_rows) { proto_avg_row(a.p, blockIdx.x); return; }
+    const int K = a.p.K, C = a.p.C;
+    if (a.tao_out && (int)threadIdx.x < C) {
+        const int c = threadIdx.x;
+        double acc = 0.0, wsum = 0.0;
+        bool any = false;
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            int cnt[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cnt[u] = (a.tcnt && k0 + u < K) ? a.tcnt[(k0 + u) * C + c] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                if (k < K && ((a.neg[k] >> c) & 1u)) {
+                    const double t = __ddiv_rn((double)cnt[u], (double)a.rows[k]);
+                    acc = __dadd_rn(acc, __dmul_rn(t, a.w[k]));
+                    wsum = __dadd_rn(wsum, a.w[k]);
+                    any = true;
+                }
+            }
+        }
+        a.tao_out[c] = any ? __ddiv_rn(acc, wsum) : 1.0;
+    }
+    if (a.counters_out) {
+        for (int j = threadIdx.x; j < a.J; j += blockDim.x) {
+            double s = 0.0;
+            for (int k0 = 0; k0 < K; k0 += 8) {
+                long long v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (k0 + u < K) ? a.counters[k0 + u][j] : 0ll;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < K) s += (double)v[u] * a.w[k0 + u];
+            }
+            a.counters_out[j] = (float)(int64_t)s / (float)a.total;
+        }
     }
 }
 
@@ -499,6 +559,38 @@ extern "C" int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, int 
         a.class_div[c] = (float)wsum;
     }
     proto_avg_kernel<<<rows_per_class * C, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status();
+}
+
+extern "C" int fmlp_agg_tails_local_f32(const float* protos, int K, int C, int D, const double* weights,
+                                        const uint64_t* class_clients, float* proto_out, const int32_t* tcnt,
+                                        const int64_t* rows, const uint32_t* neg, const int64_t* const* counters, int J,
+                                        double total_weight, double* tao_out, float* counters_out, fmlp_stream_t stream) {
+    if (!protos || !weights || !class_clients || !proto_out || C < 1 || C > FMLP_MAX_CLASSES || D < 1 || J < 0 ||
+        check_k(K) != FMLP_OK || !(total_weight > 0.0))
+        return FMLP_ERR_BAD_ARG;
+    if (tao_out && (!rows || !neg)) return FMLP_ERR_BAD_ARG;
+    if (J > 0 && (!counters || !counters_out)) return FMLP_ERR_BAD_ARG;
+    AggTailsArgs a;
+    a.p.protos = protos; a.p.out = proto_out; a.p.K = K; a.p.C = C; a.p.D = D; a.p.rpc = 2;
+    for (int i = 0; i < FMLP_MAX_CLIENTS; ++i) {
+        a.p.w[i] = i < K ? (float)weights[i] : 0.f;
+        a.w[i] = i < K ? weights[i] : 0.0;
+        a.rows[i] = (i < K && rows && rows[i] > 0) ? rows[i] : 1;
+        a.neg[i] = (i < K && neg) ? neg[i] : 0u;
+        a.counters[i] = (i < K && J > 0) ? counters[i] : nullptr;
+        if (i < K && J > 0 && !counters[i]) return FMLP_ERR_BAD_ARG;
+    }
+    for (int c = 0; c < FMLP_MAX_CLASSES; ++c) {
+        a.p.class_clients[c] = c < C ? class_clients[c] : 0ull;
+        double wsum = 0.0;
+        for (int i = 0; i < K; ++i)
+            if (c < C && ((class_clients[c] >> i) & 1ull)) wsum += weights[i];
+        a.p.class_div[c] = (float)wsum;
+    }
+    a.tcnt = tcnt; a.tao_out = tao_out; a.counters_out = J > 0 ? counters_out : nullptr; a.total = total_weight; a.J = J;
+    const int tail_cta = (tao_out || J > 0) ? 1 : 0;
+    agg_tails_local_kernel<<<2 * C + tail_cta, 256, 0, (cudaStream_t)stream>>>(a);
     return launch_status();
 }
 

@@ -68,6 +68,9 @@ struct SimArgs {
 #ifndef FMLP_SIM_RT_LARGE
 #define FMLP_SIM_RT_LARGE 2
 #endif
+#ifndef FMLP_SIM_TABLE_FIRST
+#define FMLP_SIM_TABLE_FIRST 1
+#endif
 
 template <int NPAIR, bool FOLD>
 struct SimCfg {
@@ -81,6 +84,16 @@ struct SimCfg {
     static constexpr int STAGE_BYTES = ROWS * 128;                        // one box: ROWS x 32 floats
     static constexpr int PV = NV + 1;                                     // partial values per row
 };
+
+#ifdef FMLP_SIM_TRACE
+// tuning builds only (tools/exp_sim.cu): per-CTA time stamps of the last launch, [CTA][8] =
+// {globaltimer at entry, table ready, first tile done, loop done, clock64 at the same four points}
+__device__ unsigned long long g_sim_trace[160 * 8 + 8];
+__device__ __forceinline__ unsigned long long sim_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SIM_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 160) { g_sim_trace[blockIdx.x * 8 + (i)] = sim_gtime(); g_sim_trace[blockIdx.x * 8 + 4 + (i)] = clock64(); } } while (0)
+#else
+#define SIM_STAMP(i) do {} while (0)
+#endif
 
 __device__ __forceinline__ void fma2(u64& acc, u64 a, u64 b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
@@ -129,6 +142,9 @@ __global__ void __launch_bounds__(256) sim_quad_table_kernel(const float* __rest
                                                              int npair, const __grid_constant__ SimArgs a,
                                                              float* __restrict__ table) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the main kernel may start its prologue now
+#ifdef FMLP_SIM_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_sim_trace[160 * 8] = sim_gtime();
+#endif
     __shared__ float red[2][8];
     __shared__ float nrm[2];
     const int q = blockIdx.x;
@@ -158,6 +174,10 @@ __global__ void __launch_bounds__(256) sim_quad_table_kernel(const float* __rest
         }
     }
     if (threadIdx.x < 2) table[(size_t)nv * NG * 32 + 2 * q + threadIdx.x] = nrm[threadIdx.x];
+#ifdef FMLP_SIM_TRACE
+    __syncthreads();
+    if (threadIdx.x == 0) g_sim_trace[160 * 8 + 1 + (blockIdx.x == 0 ? 0 : 1)] = sim_gtime();
+#endif
 }
 
 template <int NPAIR, bool FOLD>
@@ -177,6 +197,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    SIM_STAMP(0);
     // the selection kernel behind this one is a programmatic dependent launch too: let it be set up now
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -204,19 +225,33 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
         if (warp == 0) sim_mbar_init(tbar_u32, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < S; ++s) issue();     // the ring fills while the table kernel finishes
-        if (warp == 0) {
-            // the class vectors come from the table kernel this launch programmatically depends on
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            const uint32_t bytes = (uint32_t)((NG * 32 * NV + ((2 * NPAIR + 3) & ~3)) * sizeof(float));
-            sim_mbar_expect_tx(tbar_u32, bytes);
-            // sP, sPart, sNorm are laid out so that table = [sP | norms] lands with two copies
-            sim_bulk_g2s(sim_smem_u32(sP), a.table, (uint32_t)(NG * 32 * NV * sizeof(float)), tbar_u32);
-            sim_bulk_g2s(sim_smem_u32(sNorm), a.table + (size_t)NG * 32 * NV, (uint32_t)(((2 * NPAIR + 3) & ~3) * sizeof(float)), tbar_u32);
-        }
     }
+    auto load_table = [&]() {
+        // the class vectors come from the table kernel this launch programmatically depends on
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const uint32_t bytes = (uint32_t)((NG * 32 * NV + ((2 * NPAIR + 3) & ~3)) * sizeof(float));
+        sim_mbar_expect_tx(tbar_u32, bytes);
+        // sP, sPart, sNorm are laid out so that table = [sP | norms] lands with two copies
+        sim_bulk_g2s(sim_smem_u32(sP), a.table, (uint32_t)(NG * 32 * NV * sizeof(float)), tbar_u32);
+        sim_bulk_g2s(sim_smem_u32(sNorm), a.table + (size_t)NG * 32 * NV, (uint32_t)(((2 * NPAIR + 3) & ~3) * sizeof(float)), tbar_u32);
+    };
+#if FMLP_SIM_TABLE_FIRST
+    // The table copy goes to the TMA unit AHEAD of the feature boxes: queued behind W*S boxes of cold HBM reads it
+    // landed 3.3 us after kernel entry (r02 trace), although the table kernel had long finished — by the time
+    // this grid's CTAs start, griddepcontrol.wait returns at once, so nothing is lost by waiting first.
+    if (threadIdx.x == 0) load_table();
+    __syncthreads();
+    if (lane == 0)
+        for (int s = 0; s < S; ++s) issue();
+#else
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) issue();     // the ring fills while the table kernel finishes
+        if (warp == 0) load_table();
+    }
+#endif
     __syncthreads();                              // barrier inits are visible to every waiter
     sim_mbar_wait(tbar_u32, 0);
+    SIM_STAMP(1);
 
     // lane's row inside a box: 128 bytes per row, 16-byte chunk k of row r sits at chunk k ^ (r & 7)
     const uint32_t row_off = (uint32_t)lane * 128u + ((uint32_t)(lane & 7) << 4);
@@ -313,7 +348,11 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
                 }
             }
         }
+#ifdef FMLP_SIM_TRACE
+        if (tile == blockIdx.x) SIM_STAMP(2);
+#endif
     }
+    SIM_STAMP(3);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
@@ -434,6 +473,12 @@ static int dispatch_sim(int npair, SimArgs& a, const SimFeat& ft, cudaStream_t s
 }  // namespace fmlp
 
 using namespace fmlp;
+
+#ifdef FMLP_SIM_TRACE
+extern "C" int fmlp_sim_trace_read(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_sim_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 extern "C" size_t fmlp_tag_sim_ws_bytes(int C, int D) {
     if (C < 1 || C > FMLP_MAX_CLASSES || D < 1) return 0;

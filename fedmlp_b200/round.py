@@ -114,6 +114,7 @@ class ClientShard:
         self.tagger = TagBatch(self.seg_rows, self.C, self.active, self.missing, dataset_idx=dataset_idx,
                                device=self.device)
         self._plan = None
+        self._tail_stream = None
 
     def plan(self, D, P) -> _Plan:
         if self._plan is None or self._plan.D != D or self._plan.P != P:
@@ -217,16 +218,13 @@ class ClientShard:
                 J = int(counters[0].numel()) if counters else 0
                 if J > 1024:
                     raise ValueError("at most 1024 int64 counters")
-                # FedAvg_proto (utils/FedAvg.py:72-93): the bit-exact single-GPU kernel on the clients' prototypes
-                check(lib.fmlp_proto_avg_f32(pl.proto.data_ptr(), S, C, D, 2, cabi.f64_array(weights), pl.class_active,
-                                             pl.proto_glob.data_ptr(), sb), "fmlp_proto_avg_f32")
-                # FedAvg_tao (:51-70, float64) and the int64 counters (:9-13): pack the sums, finalize
-                check(lib.fmlp_agg_tail_pack_f64(pl.tcnt.data_ptr(), S, C, cabi.f64_array(weights), pl.sizes, pl.active,
-                                                 pl.missing, cabi.ptr_array([c.data_ptr() for c in counters]) if J else None,
-                                                 J, pl.tail.data_ptr(), sb), "fmlp_agg_tail_pack_f64")
-                check(lib.fmlp_agg_finalize_f32(None, pl.tail.data_ptr(), C, 0, J, float(divisor), None,
-                                                pl.tao.data_ptr(), pl.counters.data_ptr() if J else None, sb),
-                      "fmlp_agg_finalize_f32")
+                # FedAvg_proto (utils/FedAvg.py:72-93, bit-exact), FedAvg_tao (:51-70, float64) and the int64
+                # counters (:9-13) in one launch (three dependent launches until round 2)
+                check(lib.fmlp_agg_tails_local_f32(pl.proto.data_ptr(), S, C, D, cabi.f64_array(weights), pl.class_active,
+                                                   pl.proto_glob.data_ptr(), pl.tcnt.data_ptr(), pl.sizes, pl.missing,
+                                                   cabi.ptr_array([c.data_ptr() for c in counters]) if J else None, J,
+                                                   float(divisor), pl.tao.data_ptr(), pl.counters.data_ptr() if J else None,
+                                                   sb), "fmlp_agg_tails_local_f32")
                 out["proto_glob"], out["tao"] = pl.proto_glob, pl.tao
                 out["counters"] = pl.counters[:J] if J else None
 
@@ -271,6 +269,11 @@ class ClientShard:
                 {"sim": sim_stage, "proto": lambda: proto_stage(stream), "fedavg": lambda: aggregate_stage(stream),
                  "tail": select_fill_loss}[only]()
                 return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz, protos, out["glob"], ev)
+            tail_stream = None
+            if side_stream is not None and agg_stream is None and aggregate_tails and tails_fn is None and aggregate_fn is None:
+                if self._tail_stream is None:
+                    self._tail_stream = torch.cuda.Stream(device=dev)
+                tail_stream = self._tail_stream
             mark("start")
             split3 = side_stream is not None and agg_stream is not None and aggregate_fn is None
             if split3:
@@ -285,7 +288,15 @@ class ClientShard:
                 side_stream.wait_stream(stream)
                 with torch.cuda.stream(side_stream):
                     proto_stage(side_stream)
-                    aggregate_stage(side_stream)
+                    if aggregate_fn is None and tail_stream is not None:
+                        # the small tails only need the prototypes: they leave the chain here and run next to the
+                        # parameter aggregation instead of behind it (latency-bound, 7 us at the end of the round)
+                        tail_stream.wait_stream(side_stream)
+                        with torch.cuda.stream(tail_stream):
+                            tails_stage(tail_stream)
+                        params_stage(side_stream)
+                    else:
+                        aggregate_stage(side_stream)
             sim_stage()
             mark("sim")
             if side_stream is not None:
@@ -293,6 +304,8 @@ class ClientShard:
                 stream.wait_stream(side_stream)
                 if split3:
                     stream.wait_stream(agg_stream)
+                elif aggregate_fn is None and tail_stream is not None:
+                    stream.wait_stream(tail_stream)
             else:
                 proto_stage(stream)
                 aggregate_stage(stream)

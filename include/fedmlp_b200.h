@@ -177,6 +177,19 @@ int fmlp_proto_avg_f32(const float* protos, int K, int C, int D, int rows_per_cl
 /* rows_per_class = 2: the layout above (FedAvg_proto).  rows_per_class = 1: protos [K][C][D], one row
  * per class = utils/FedAvg.py:95-103 `FedAvg_rela`.                                            */
 
+/* All the small tails of the single-GPU server aggregation (main.py:218-234) in ONE launch: FedAvg_proto
+ * (utils/FedAvg.py:72-93, as fmlp_proto_avg_f32 with rows_per_class = 2), FedAvg_tao over the clients that miss
+ * each class (:51-70, IEEE double in the reference's order; t_k[c] = tcnt[k][c] / rows[k] as at
+ * utils/local_training.py:1000,1249; 1.0 for an empty list) and the int64 BatchNorm counters
+ * (FedAvg.py:9-13: sum_k n_k * counter_k, then the float32 divide by total_weight).
+ *   protos device [K][2C][D]; weights / rows / neg (missing-class masks) host [K]; class_clients host [C];
+ *   tcnt device [K][C] int32; counters host [K] device pointers to J int64 each (NULL iff J == 0);
+ *   proto_out device [2C][D]; tao_out device [C] double (NULL = skip); counters_out device [J] float32.   */
+int fmlp_agg_tails_local_f32(const float* protos, int K, int C, int D, const double* weights,
+                             const uint64_t* class_clients, float* proto_out, const int32_t* tcnt,
+                             const int64_t* rows, const uint32_t* neg, const int64_t* const* counters, int J,
+                             double total_weight, double* tao_out, float* counters_out, fmlp_stream_t stream);
+
 /* Difficulty aggregation, replaces utils/FedAvg.py:51-70 `FedAvg_tao` (float64, bit-identical:
  * same operation order, IEEE double mul/add/div):
  *   class_clients != NULL: out[c] = sum_{i in list(c)} t[i][c]*w_i / sum w_i, 1.0 for an empty list

@@ -12,9 +12,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.mark.parametrize("two_streams", [False, True])
 @pytest.mark.parametrize("mode", ["pair", "folded"])
-def test_round_hot_path_matches_per_client_oracle(lib, mode):
+def test_round_hot_path_matches_per_client_oracle(lib, mode, two_streams):
+    """two_streams: the DAG form bench.py replays ({sim, select, fill+loss} || {prototypes, FedAvg} with the small
+    aggregation tails forked off behind the prototype pass) must give the same results as the serial order."""
     from fedmlp_b200.round import ClientShard
+    side = torch.cuda.Stream(device=DEV) if two_streams else None
 
     C, D, P = 5, 256, 10007 + 1          # P multiple of 4
     sizes = [700, 333, 1201, 64]
@@ -36,7 +40,8 @@ def test_round_hot_path_matches_per_client_oracle(lib, mode):
         counters = [torch.arange(7, dtype=torch.int64) * (s + 1) + 100 * rnd for s in range(S)]
         res = shard.round_hot_path(feat.to(DEV), proto.to(DEV), logits.to(DEV), zg.to(DEV), labels.to(DEV),
                                    feat2.to(DEV), logits2.to(DEV), [f.to(DEV) for f in flats], sizes,
-                                   aggregate_tails=True, counters=[c.to(DEV) for c in counters])
+                                   aggregate_tails=True, counters=[c.to(DEV) for c in counters], side_stream=side)
+        torch.cuda.synchronize()
         t = res.protos.t()
         for s, n in enumerate(sizes):
             r0, r1 = shard.seg_rows[s], shard.seg_rows[s + 1]

@@ -12,6 +12,9 @@
 #include "fedmlp_b200.h"
 
 namespace fmlp { unsigned long long g_launch_count = 0; }
+#ifdef FMLP_SIM_TRACE
+extern "C" int fmlp_sim_trace_read(unsigned long long* host, int n);
+#endif
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); exit(1); } } while (0)
 
@@ -128,6 +131,29 @@ int main(int argc, char** argv) {
             }
             cudaGetLastError();
         }
+#ifdef FMLP_SIM_TRACE
+        {   // per-CTA time stamps of ONE isolated launch (ns relative to the first CTA's entry)
+            CK(cudaDeviceSynchronize());
+            fmlp_tag_sim_f32(feat, D, D, proto, C, S, rows.data(), missing.data(), sim, N, mode, ws, ws_bytes, 0);
+            CK(cudaDeviceSynchronize());
+            std::vector<unsigned long long> tr(160 * 8 + 8);
+            fmlp_sim_trace_read(tr.data(), (int)tr.size());
+            unsigned long long t0 = tr[0];
+            for (int b = 0; b < 148; ++b) t0 = tr[b * 8] < t0 ? tr[b * 8] : t0;     // first CTA entry
+            double mn[4] = {1e18, 1e18, 1e18, 1e18}, mx[4] = {0, 0, 0, 0}, av[4] = {0, 0, 0, 0};
+            const int ncta = 148;
+            for (int b = 0; b < ncta; ++b)
+                for (int i = 0; i < 4; ++i) {
+                    const double v = (double)(long long)(tr[b * 8 + i] - t0);
+                    mn[i] = v < mn[i] ? v : mn[i]; mx[i] = v > mx[i] ? v : mx[i]; av[i] += v / ncta;
+                }
+            printf("{\"trace\": \"%s\", \"table_cta0_done_ns\": %lld, \"table_other_done_ns\": %lld", mode ? "folded" : "pair",
+                   (long long)(tr[160 * 8 + 1] - t0), (long long)(tr[160 * 8 + 2] - t0));
+            const char* nm[4] = {"entry", "table_ready", "first_tile_done", "loop_done"};
+            for (int i = 0; i < 4; ++i) printf(", \"%s_ns\": [%.0f, %.0f, %.0f]", nm[i], mn[i], av[i], mx[i]);
+            printf("}\n");
+        }
+#endif
         const double bytes = 4.0 * N * D + 8.0 * C * D + 4.0 * (C - 1) * N;
         printf("{\"variant\": \"%s\", \"N\": %lld, \"D\": %d, \"C\": %d, \"S\": %d, \"mode\": \"%s\", \"us\": %.2f, \"us_graph\": %.2f, \"gbs\": %.1f, "
                "\"frac_6448\": %.3f, \"max_abs_err\": %.3g, \"bad\": %lld, \"checked\": %lld, \"stages_env\": \"%s\"}\n",
