@@ -190,226 +190,6 @@ __global__ void __launch_bounds__(512, NA == 1 ? 2 : 1) proto_accum_kernel(const
     }
 }
 
-// ---- round-2 accumulate kernel: TMA row stages ------------------------------------------------
-// The register-staged kernel above keeps 8 x 16 B per thread in flight (128 KB per SM with 32 warps) and
-// reached 0.83 of the HBM roof however lean its loop was made (r02: 61 -> 15 instructions per row changed
-// nothing: it is bound by bytes in flight per warp slot, not by issue).  Here the rows travel global ->
-// shared as bulk copies (cp.async.bulk, SASS UBLKCP) into a ring of `n_stages` stages of kProtoStageRows
-// whole rows, issued by one producer lane and tracked by mbarriers: up to ~190 KB per SM in flight cost
-// no registers and no issue slots.  Consumer thread t owns float4 column t of every row (one conflict-free
-// LDS.128 per row) and keeps the label-0 / label-1 sums in registers exactly as before; a stage never
-// crosses a segment boundary, partial sums / counts go to the same (CTA, segment) slots, so the finalize
-// kernel is unchanged.  One CTA per SM, contiguous row range per CTA (one balanced wave).
-constexpr int kProtoStageRows = 8;
-constexpr int kProtoLabelChunk = 1024;   // rows whose labels are staged in shared memory at a time (multiple of the stage rows)
-
-__device__ __forceinline__ uint32_t proto_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void proto_mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void proto_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void proto_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void proto_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void proto_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// barrier among the consumer warps only (the producer warp runs ahead on its own)
-__device__ __forceinline__ void proto_consumer_sync(int n_threads) {
-    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
-}
-
-// Next non-empty part [r0, r1) of this CTA's row range that lies in ONE segment.
-__device__ __forceinline__ bool proto_next_part(const SegTable& seg, int& s, int64_t& row, int64_t cta_end, int64_t& r0, int64_t& r1) {
-    if (row >= cta_end) return false;
-    while (s < seg.S - 1 && seg.rows[s + 1] <= row) ++s;
-    r0 = row;
-    r1 = min(seg.rows[s + 1], cta_end);
-    row = r1;
-    return true;
-}
-
-template <int NA, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT <= 352 ? (NA == 1 ? 4 : 2) : 1) proto_accum_tma_kernel(const __grid_constant__ ProtoArgs a, int n_stages,
-                                                                  int n_cons_warps, int copy_mode) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finalize kernel is a programmatic dependent launch
-    constexpr int R = kProtoStageRows;
-    extern __shared__ __align__(128) unsigned char proto_smem[];
-    __shared__ int s_t[FMLP_MAX_CLASSES];
-    const int D = a.D;
-    const size_t stage_bytes = (size_t)R * D * sizeof(float);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(proto_smem + (size_t)n_stages * stage_bytes);   // full[n], empty[n]
-    float* s_y = reinterpret_cast<float*>(bars + 2 * n_stages);                                  // [NA][kProtoLabelChunk]
-    const uint32_t full_u32 = proto_smem_u32(bars), empty_u32 = full_u32 + 8u * n_stages;
-    const uint32_t ring_u32 = proto_smem_u32(proto_smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = a.seg.S;
-    const int64_t n_total = a.seg.rows[S];
-    const int64_t cta_begin = (int64_t)blockIdx.x * a.rows_per_cta;
-    const int64_t cta_end = min(n_total, cta_begin + a.rows_per_cta);
-    if (cta_begin >= n_total) return;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < n_stages; ++i) { proto_mbar_init(full_u32 + 8u * i, 1); proto_mbar_init(empty_u32 + 8u * i, n_cons_warps); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    int s = find_segment(a.seg.rows, S, cta_begin);
-    int64_t row = cta_begin, r0, r1;
-
-    if (warp == n_cons_warps) {
-        // ---- producer warp: walks the same stage sequence as the consumers.  copy_mode 0: lane 0 issues one bulk
-        // copy per stage (dense rows only); 1: lane 0 issues one copy per row; 2: lane u issues row u's copy.
-        const bool dense = a.ld_feat == D;
-        const int mode = (copy_mode == 0 && !dense) ? 1 : copy_mode;
-        int slot = 0;
-        uint32_t round = 0;              // how many times the ring has wrapped
-        while (proto_next_part(a.seg, s, row, cta_end, r0, r1)) {
-            for (int64_t r = r0; r < r1; r += R) {
-                const int n = (int)min((int64_t)R, r1 - r);
-                const uint32_t bar = full_u32 + 8u * slot;
-                const uint32_t dst = ring_u32 + (uint32_t)(slot * stage_bytes);
-                if (lane == 0) {
-                    if (round > 0) proto_mbar_wait(empty_u32 + 8u * slot, (round - 1) & 1u);
-                    proto_mbar_expect_tx(bar, (uint32_t)(n * D * sizeof(float)));
-                    if (mode == 0) {
-                        proto_bulk_g2s(dst, a.feat + r * a.ld_feat, (uint32_t)(n * D * sizeof(float)), bar);
-                    } else if (mode == 1) {
-                        for (int u = 0; u < n; ++u)
-                            proto_bulk_g2s(dst + (uint32_t)(u * D * sizeof(float)), a.feat + (r + u) * a.ld_feat, (uint32_t)(D * sizeof(float)), bar);
-                    }
-                }
-                if (mode == 2) {
-                    __syncwarp();
-                    if (lane < n)
-                        proto_bulk_g2s(dst + (uint32_t)(lane * D * sizeof(float)), a.feat + (r + lane) * a.ld_feat, (uint32_t)(D * sizeof(float)), bar);
-                }
-                if (++slot == n_stages) { slot = 0; ++round; }
-            }
-        }
-        return;
-    }
-
-    // ---- consumers
-    const int n_cons = n_cons_warps * 32;
-    const int col = threadIdx.x * 4;
-    const bool col_ok = col < D;
-    const float* my_col = reinterpret_cast<const float*>(proto_smem) + (col_ok ? col : 0);
-    int slot = 0;
-    uint32_t parity = 0;
-    // Labels (active classes only) of up to kProtoLabelChunk rows are staged in shared memory, across segment
-    // boundaries: a per-stage __ldg missed to HBM under full load (~2 us) once per stage and halved the rate, a
-    // staging pass per segment part stalled the CTA once more in the middle of its range (r02).  A CTA's whole
-    // range is normally one chunk, requested at kernel start together with the first row stages.
-    int64_t y_base = cta_begin, y_end = cta_begin;           // rows [y_base, y_end) are staged
-    auto stage_labels = [&](int64_t from) {
-        proto_consumer_sync(n_cons);                         // the previous chunk's readers are done
-        y_base = from;
-        y_end = min(cta_end, from + kProtoLabelChunk);
-        const int n_chunk = (int)(y_end - y_base);
-        for (int idx = threadIdx.x; idx < n_chunk; idx += n_cons) {
-            const int64_t rw = y_base + idx;
-            const uint32_t act = a.seg.mask_a[find_segment(a.seg.rows, S, rw)];
-            uint32_t m = act;
-#pragma unroll
-            for (int i = 0; i < NA; ++i) {
-                float v = -1.f;
-                if (m) { v = __ldg(a.labels + rw * a.C + (__ffs(m) - 1)); m &= m - 1; }
-                s_y[i * kProtoLabelChunk + idx] = v;
-            }
-        }
-        proto_consumer_sync(n_cons);
-    };
-    while (proto_next_part(a.seg, s, row, cta_end, r0, r1)) {
-        float4 acc[NA][2];
-        int n_lab[NA][2];
-#pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            acc[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            n_lab[i][0] = 0; n_lab[i][1] = 0;
-        }
-        for (int64_t r = r0; r < r1; r += R) {
-            const int n = (int)min((int64_t)R, r1 - r);
-            if (r + n > y_end) stage_labels(r);
-            const int yo = (int)(r - y_base);
-            proto_mbar_wait(full_u32 + 8u * slot, parity);
-            const float* src = my_col + (size_t)slot * R * D;
-#pragma unroll
-            for (int u = 0; u < R; ++u) {
-                if (u < n) {
-                    const float4 f = *reinterpret_cast<const float4*>(src + (size_t)u * D);
-#pragma unroll
-                    for (int i = 0; i < NA; ++i) {
-                        // labels == 0 / labels == 1 exactly as torch.where(labels[:, cls] == k) (:985-986)
-                        const float y = s_y[i * kProtoLabelChunk + yo + u];
-                        if (y == 0.f) {
-                            acc[i][0].x += f.x; acc[i][0].y += f.y; acc[i][0].z += f.z; acc[i][0].w += f.w;
-                            n_lab[i][0]++;
-                        } else if (y == 1.f) {
-                            acc[i][1].x += f.x; acc[i][1].y += f.y; acc[i][1].z += f.z; acc[i][1].w += f.w;
-                            n_lab[i][1]++;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) proto_mbar_arrive(empty_u32 + 8u * slot);
-            if (++slot == n_stages) { slot = 0; parity ^= 1u; }
-        }
-
-        const int64_t slot_id = (int64_t)blockIdx.x + s;
-        if (col_ok) {
-#pragma unroll
-            for (int i = 0; i < NA; ++i) {
-                float* dst = a.partial + ((slot_id * NA + i) * 2) * (int64_t)D + col;
-                *reinterpret_cast<float4*>(dst) = acc[i][0];
-                *reinterpret_cast<float4*>(dst + D) = acc[i][1];
-            }
-        }
-        int32_t* pc = a.pcount + slot_id * kProtoCountStride;
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int i = 0; i < NA; ++i) { pc[2 * i] = n_lab[i][0]; pc[2 * i + 1] = n_lab[i][1]; }
-        }
-        // confident-prediction counts (:995-996, :1239): #{p < L or p > U}
-        if (a.do_t) {
-            const uint32_t tmask = a.seg.mask_b[s];
-            proto_consumer_sync(n_cons);
-            if (threadIdx.x < FMLP_MAX_CLASSES) s_t[threadIdx.x] = 0;
-            proto_consumer_sync(n_cons);
-            if (a.logits != nullptr && tmask != 0u) {
-                const int n_el = (int)(r1 - r0) * a.C;                // one CTA's row range: far below 2^31
-                const float* z = a.logits + r0 * a.C;
-                for (int e = threadIdx.x; e < n_el; e += n_cons) {
-                    const int c = e % a.C;
-                    if ((tmask >> c) & 1u) {
-                        const float v = z[e];
-                        const float p = a.logits_are_probs ? v : sigmoid_ref(v);
-                        if (p < a.L || p > a.U) atomicAdd(&s_t[c], 1);
-                    }
-                }
-            }
-            proto_consumer_sync(n_cons);
-            if (threadIdx.x < a.C) pc[2 * kProtoMaxActive + threadIdx.x] = s_t[threadIdx.x];
-        }
-    }
-}
-
 struct ProtoFinArgs {
     const float* partial;
     const int32_t* pcount;
@@ -518,39 +298,6 @@ static int proto_ctas_per_sm(int threads) {
     return cached;
 }
 
-static bool proto_use_tma() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("FMLP_PROTO_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
-}
-// shared memory the row ring may take: 200 KB by default (a CTA of a concurrent kernel with a little shared
-// memory can still share the SM), FMLP_PROTO_SMEM_KB overrides (64..227)
-static size_t proto_tma_smem_budget() {
-    static size_t v = 0;
-    if (v == 0) {
-        v = 200u * 1024u;
-        if (const char* e = getenv("FMLP_PROTO_SMEM_KB")) { int kb = atoi(e); if (kb >= 16 && kb <= 227) v = (size_t)kb * 1024u; }
-    }
-    return v;
-}
-
-template <int NA>
-static int launch_proto_tma(const ProtoArgs& a, unsigned gx, int threads, size_t smem, int n_stages, int cons_warps, cudaStream_t st) {
-    // three register budgets: up to 352 threads (D <= 1280; several CTAs per SM), up to 512 (D <= 1920) and up to 1024
-    static size_t configured[3] = {0, 0, 0};   // per template instance
-    const int big = threads > 512 ? 2 : (threads > 352 ? 1 : 0);
-    auto kern = big == 2 ? proto_accum_tma_kernel<NA, 1024> : (big == 1 ? proto_accum_tma_kernel<NA, 512> : proto_accum_tma_kernel<NA, 352>);
-    if (smem > 48u * 1024u && smem > configured[big]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[big] = smem;
-    }
-    static int copy_mode = -1;
-    if (copy_mode < 0) { const char* e = getenv("FMLP_PROTO_COPY"); copy_mode = e ? atoi(e) : 0; if (copy_mode < 0 || copy_mode > 2) copy_mode = 0; }
-    kern<<<gx, threads, smem, st>>>(a, n_stages, cons_warps, copy_mode);
-    return launch_status();
-}
-
 }  // namespace fmlp
 
 using namespace fmlp;
@@ -623,41 +370,13 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
         a.do_t = (first && logits != nullptr && tcnt != nullptr) ? 1 : 0;
         const int NA = na_max <= 1 ? 1 : (na_max == 2 ? 2 : 4);
         // one balanced wave: as many CTAs as can be co-resident, each with a contiguous row range
-        // TMA row-stage kernel (one CTA per SM) whenever a CTA can hold whole rows: D / 4 <= 992 consumer threads
-        // and at least two stages of kProtoStageRows rows in shared memory; otherwise the register-staged kernel.
-        const int cons_warps = (nvec + 31) / 32;
-        const size_t stage_bytes = (size_t)kProtoStageRows * D * sizeof(float);
-        const size_t label_bytes = (size_t)kProtoMaxActive * kProtoLabelChunk * sizeof(float);
-        static int tma_ctas = 0;            // CTAs per SM sharing the shared-memory budget (FMLP_PROTO_CTAS, 1..4)
-        if (tma_ctas == 0) { const char* e = getenv("FMLP_PROTO_CTAS"); tma_ctas = e ? atoi(e) : 1; if (tma_ctas < 1 || tma_ctas > 4) tma_ctas = 1; }
-        int n_stages = (int)((proto_tma_smem_budget() / tma_ctas - 1024 - label_bytes) / (stage_bytes + 16));
-        if (n_stages > 12) n_stages = 12;
-        const bool use_tma = proto_use_tma() && cons_warps <= 31 && n_stages >= 2;
-        int64_t rpc;
-        if (use_tma) {
-            int64_t gx = (int64_t)sms * tma_ctas;
-            if (gx > (n_total + kProtoStageRows - 1) / kProtoStageRows) gx = (n_total + kProtoStageRows - 1) / kProtoStageRows;
-            if (gx < 1) gx = 1;
-            rpc = (n_total + gx - 1) / gx;
-            rpc = (rpc + kProtoStageRows - 1) / kProtoStageRows * kProtoStageRows;
-            a.rows_per_cta = rpc;
-            if (n_total > 0) {
-                gx = (n_total + rpc - 1) / rpc;
-                const size_t smem = (size_t)n_stages * stage_bytes + (size_t)n_stages * 16 + label_bytes;
-                const int tthreads = (cons_warps + 1) * 32;
-                rc = NA == 1 ? launch_proto_tma<1>(a, (unsigned)gx, tthreads, smem, n_stages, cons_warps, st)
-                   : NA == 2 ? launch_proto_tma<2>(a, (unsigned)gx, tthreads, smem, n_stages, cons_warps, st)
-                             : launch_proto_tma<4>(a, (unsigned)gx, tthreads, smem, n_stages, cons_warps, st);
-                if (rc != FMLP_OK) return rc;
-            }
-        } else {
         int per_sm = NA == 1 ? proto_ctas_per_sm<1>(threads) : (NA == 2 ? proto_ctas_per_sm<2>(threads) : proto_ctas_per_sm<4>(threads));
         int64_t gx = (int64_t)sms * per_sm / gy;
         if (gx < 1) gx = 1;
         const int64_t min_rows = 2 * kProtoUnroll;
         if (gx > (n_total + min_rows - 1) / min_rows) gx = (n_total + min_rows - 1) / min_rows;
         if (gx < 1) gx = 1;
-        rpc = (n_total + gx - 1) / gx;
+        int64_t rpc = (n_total + gx - 1) / gx;
         rpc = (rpc + kProtoUnroll - 1) / kProtoUnroll * kProtoUnroll;
         if (rpc < kProtoUnroll) rpc = kProtoUnroll;
         a.rows_per_cta = rpc;
@@ -669,7 +388,6 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
             else proto_accum_kernel<4><<<grid, threads, 0, st>>>(a);
             rc = launch_status();
             if (rc != FMLP_OK) return rc;
-        }
         }
         ProtoFinArgs f;
         f.partial = a.partial; f.pcount = a.pcount; f.proto = proto; f.cnt = cnt; f.tcnt = tcnt;
