@@ -15,6 +15,7 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("FEDMLP_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"))
 
 ABI_VERSION = 3
+TUNE_PROTO_PAD_SMEM_KB, TUNE_SIM_REQUEST_SMEM_KB, TUNE_SIM_SMEM_BUDGET_KB = 0, 1, 2
 MAX_CLASSES = 32
 MAX_SEGMENTS = 64
 MAX_CLIENTS = 64
@@ -38,6 +39,8 @@ _sz = C.c_size_t
 # name -> (restype, argtypes); mirrors include/fedmlp_b200.h one to one
 SIGNATURES = {
     "fmlp_abi_version": (_i, []),
+    "fmlp_set_tuning": (_i, [_i, _i]),
+    "fmlp_get_tuning": (_i, [_i]),
     "fmlp_status_string": (C.c_char_p, [_i]),
     "fmlp_sm_count": (_i, []),
     "fmlp_launch_count": (C.c_ulonglong, []),

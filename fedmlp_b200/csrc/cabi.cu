@@ -1,7 +1,10 @@
 // cabi.cu — ABI version / status strings / device queries of libfedmlp_b200.
 #include "common.cuh"
 
-namespace fmlp { unsigned long long g_launch_count = 0; }
+namespace fmlp {
+unsigned long long g_launch_count = 0;
+int g_tuning[FMLP_TUNE_COUNT] = {-1, -1, -1};     // -1 = not set: the environment variable / built-in default applies
+}
 
 extern "C" unsigned long long fmlp_launch_count(void) { return __atomic_load_n(&fmlp::g_launch_count, __ATOMIC_RELAXED); }
 
@@ -20,3 +23,13 @@ extern "C" const char* fmlp_status_string(int code) {
 }
 
 extern "C" int fmlp_sm_count(void) { return fmlp::sm_count(); }
+
+extern "C" int fmlp_set_tuning(int knob, int value) {
+    if (knob < 0 || knob >= FMLP_TUNE_COUNT || value < -1) return FMLP_ERR_BAD_ARG;
+    __atomic_store_n(&fmlp::g_tuning[knob], value, __ATOMIC_RELAXED);
+    return FMLP_OK;
+}
+extern "C" int fmlp_get_tuning(int knob) {
+    if (knob < 0 || knob >= FMLP_TUNE_COUNT) return -1;
+    return __atomic_load_n(&fmlp::g_tuning[knob], __ATOMIC_RELAXED);
+}

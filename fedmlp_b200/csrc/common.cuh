@@ -1,6 +1,7 @@
 // common.cuh — shared device/host helpers for libfedmlp_b200 (sm_100a only).
 #pragma once
 
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,6 +31,13 @@ inline int sm_count() {
 
 // Process-wide count of kernel launches issued by this library (bench.py reports it).
 extern unsigned long long g_launch_count;
+extern int g_tuning[FMLP_TUNE_COUNT];
+// value of a tuning knob: fmlp_set_tuning() first, then the environment variable, then the default
+inline int tuning_value(int knob, const char* env, int lo, int hi, int dflt) {
+    int v = __atomic_load_n(&g_tuning[knob], __ATOMIC_RELAXED);
+    if (v < 0) { const char* e = getenv(env); v = e ? atoi(e) : dflt; }
+    return (v < lo || v > hi) ? dflt : v;
+}
 
 // Launch epilogue: surface launch-configuration errors as a positive cudaError_t.
 inline int launch_status() {

@@ -383,9 +383,21 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
         if (n_total > 0) {
             gx = (n_total + rpc - 1) / rpc;
             dim3 grid((unsigned)gx, (unsigned)gy);
-            if (NA == 1) proto_accum_kernel<1><<<grid, threads, 0, st>>>(a);
-            else if (NA == 2) proto_accum_kernel<2><<<grid, threads, 0, st>>>(a);
-            else proto_accum_kernel<4><<<grid, threads, 0, st>>>(a);
+            // scheduling knob (include/fedmlp_b200.h): unused dynamic shared memory per CTA steers co-residency with
+            // the similarity kernel of a concurrent stream
+            const size_t dsm = (size_t)tuning_value(FMLP_TUNE_PROTO_PAD_SMEM_KB, "FMLP_PROTO_PAD_SMEM_KB", 0, 56, 0) * 1024;
+            if (dsm > 48u * 1024u) {
+                static bool raised = false;
+                if (!raised) {
+                    cudaFuncSetAttribute(proto_accum_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+                    cudaFuncSetAttribute(proto_accum_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+                    cudaFuncSetAttribute(proto_accum_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+                    raised = true;
+                }
+            }
+            if (NA == 1) proto_accum_kernel<1><<<grid, threads, dsm, st>>>(a);
+            else if (NA == 2) proto_accum_kernel<2><<<grid, threads, dsm, st>>>(a);
+            else proto_accum_kernel<4><<<grid, threads, dsm, st>>>(a);
             rc = launch_status();
             if (rc != FMLP_OK) return rc;
         }

@@ -125,21 +125,21 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
             key[k] = make_comp(v[k], i) | (sd == 1 ? kSideBit : 0ull);
             if (tg[k] == 0) { ++n_cand; if (sd >= 0) valid |= 1u << k; }
         }
-    } else {
-#pragma unroll 8
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) n_cand += tag[i] == 0 ? 1 : 0;
     }
-    // visit every candidate key of this thread
-    auto for_each = [&](auto&& fn) {
+    // visit every candidate key of this thread (count_cand: the uncached path also counts its tag == 0 rows,
+    // once, in the first histogram pass — a pass of its own was one more sweep over the segment)
+    auto for_each = [&](auto&& fn, bool count_cand = false) {
+        // fn(key, ok) is called for every key slot of the thread; ok = the slot holds a candidate
         if (CACHED) {
 #pragma unroll
-            for (int k = 0; k < NK; ++k)
-                if ((valid >> k) & 1u) fn(key[k]);
+            for (int k = 0; k < NK; ++k) fn(key[k], ((valid >> k) & 1u) != 0u);
         } else {
-            // batches of 8 independent (tag, sim) loads per thread: with one dependent pair per iteration a pass
-            // over an 85,000-row client was ~80 serial L2 round trips per thread (r02: 136 us for 13 classes)
-            constexpr int U = 8;
-            for (uint32_t base = threadIdx.x; base < n; base += THREADS * U) {
+            // batches of 16 independent (tag, sim) loads per thread: with one dependent pair per iteration a pass
+            // over an 85,000-row client was ~80 serial L2 round trips per thread (r02: 136 us for 13 classes;
+            // 84 us with batches of 8, eight sweeps per item)
+            constexpr int U = 16;
+            for (uint32_t base0 = 0; base0 < n; base0 += THREADS * U) {      // same trip count for every thread
+                const uint32_t base = base0 + threadIdx.x;
                 uint8_t tg[U];
                 float v[U];
 #pragma unroll
@@ -151,10 +151,10 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (tg[u] != 0) continue;
+                    const bool cand = tg[u] == 0;
+                    if (count_cand && cand) ++n_cand;
                     const int sd = side_of(v[u]);
-                    if (sd < 0) continue;
-                    fn(make_comp(v[u], base + (uint32_t)u * THREADS) | (sd == 1 ? kSideBit : 0ull));
+                    fn(make_comp(v[u], base + (uint32_t)u * THREADS) | (sd == 1 ? kSideBit : 0ull), cand && sd >= 0);
                 }
             }
         }
@@ -164,6 +164,12 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
     unsigned long long thresh[2] = {~0ull, ~0ull};  // comp >= thresh selects; ~0 selects nothing
     int rem[2] = {0, 0};
     bool done[2] = {false, false};
+    // A side whose target bin holds at most kSmallBin keys leaves the digit loop: its bin is gathered into shared
+    // memory in ONE more sweep and the rem-th largest key found by counting.  All comps are distinct down to the
+    // row bits, so the digit loop alone always ran its six sweeps; now it is one or two plus the gather.
+    constexpr int kSmallBin = 512;
+    bool resolve[2] = {false, false};
+    int res_shift[2] = {0, 0};
     int n_side[2] = {0, 0}, want[2] = {0, 0};
 
     // digits of the 63 significant comp bits, most significant first: 5 x 11 bits + 8 bits
@@ -176,13 +182,12 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
         const unsigned long long dmask = (1ull << width) - 1ull;
         const unsigned long long pre0 = prefix[0], pre1 = prefix[1];
         const bool d0 = done[0], d1 = done[1];
-        for_each([&](unsigned long long k) {
+        for_each([&](unsigned long long k, bool ok) {
             const int sd = (int)(k >> 63);
             const unsigned long long comp = k & ~kSideBit;
-            if (sd ? d1 : d0) return;
-            if (pass == 0 || (comp >> (shift + width)) == (sd ? pre1 : pre0))
-                atomicAdd(&s_hist[sd][(int)((comp >> shift) & dmask)], 1);
-        });
+            const bool hit = ok && !(sd ? d1 : d0) && (pass == 0 || (comp >> (shift + width)) == (sd ? pre1 : pre0));
+            if (hit) atomicAdd(&s_hist[sd][(int)((comp >> shift) & dmask)], 1);
+        }, !CACHED && pass == 0);
         __syncthreads();
         // bins are visited from the top: thread t owns bins 2047-BPT*t .. 2047-BPT*t-(BPT-1)
         int h[2][BPT];
@@ -236,7 +241,43 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
                 done[sd] = true;
             } else {
                 rem[sd] = rem_in;
+                if (bin_count <= kSmallBin && shift > 0) { resolve[sd] = true; res_shift[sd] = shift; done[sd] = true; }
             }
+        }
+        __syncthreads();
+    }
+
+    // ---- small target bins: gather the keys that share the prefix, take the rem-th largest ----
+    if (resolve[0] || resolve[1]) {          // uniform across the CTA
+        unsigned long long* list = reinterpret_cast<unsigned long long*>(&s_hist[0][0]);   // [2][kSmallBin], histogram is dead
+        if (threadIdx.x < 2) s_found[threadIdx.x][0] = 0;
+        __syncthreads();
+        const unsigned long long pre0 = prefix[0], pre1 = prefix[1];
+        const int sh0 = res_shift[0], sh1 = res_shift[1];
+        const bool rs0 = resolve[0], rs1 = resolve[1];
+        for_each([&](unsigned long long k, bool ok) {
+            const int sd = (int)(k >> 63);
+            const unsigned long long comp = k & ~kSideBit;
+            if (!ok || !(sd ? rs1 : rs0)) return;
+            if ((comp >> (sd ? sh1 : sh0)) == (sd ? pre1 : pre0)) {
+                const int slot = atomicAdd(&s_found[sd][0], 1);
+                if (slot < kSmallBin) list[sd * kSmallBin + slot] = comp;
+            }
+        });
+        __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!resolve[sd]) continue;
+            const int cnt = min(s_found[sd][0], kSmallBin);
+            __syncthreads();
+            if ((int)threadIdx.x < cnt) {
+                const unsigned long long mine = list[sd * kSmallBin + threadIdx.x];
+                int rank = 0;
+                for (int j = 0; j < cnt; ++j) rank += (list[sd * kSmallBin + j] > mine) ? 1 : 0;
+                if (rank == rem[sd] - 1) *reinterpret_cast<unsigned long long*>(&s_warp[sd]) = mine;
+            }
+            __syncthreads();
+            thresh[sd] = s_warp[sd];
         }
         __syncthreads();
     }
@@ -246,10 +287,10 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
     if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(&s_count[2], n_cand);
     {
         const unsigned long long t0 = thresh[0], t1 = thresh[1];
-        for_each([&](unsigned long long k) {
+        for_each([&](unsigned long long k, bool ok) {
             const int sd = (int)(k >> 63);
             const unsigned long long comp = k & ~kSideBit;
-            if (comp >= (sd ? t1 : t0)) {
+            if (ok && comp >= (sd ? t1 : t0)) {
                 const int slot = atomicAdd(&s_count[sd], 1);
                 if (slot < a.cap) a.cand[((int64_t)item * 2 + sd) * a.cap + slot] = comp;
                 tag[0xFFFFFFFFu - (uint32_t)(comp & 0xFFFFFFFFull)] = (uint8_t)(1 + sd);

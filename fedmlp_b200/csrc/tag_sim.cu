@@ -405,19 +405,20 @@ static int launch_sim(SimArgs& a, const SimFeat& ft, cudaStream_t st) {
     // a launch whose fixed part alone needs more falls back to two stages within the hard limit.
     const size_t hard = 227u * 1024u;
     static int max_stages = 0;
-    static size_t soft = 0;
     if (max_stages == 0) {
         max_stages = 8;
-        soft = 200u * 1024u;
         if (const char* e = getenv("FMLP_SIM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 16) max_stages = v; }
-        if (const char* e = getenv("FMLP_SIM_SMEM_KB")) { int v = atoi(e); if (v >= 64 && v <= 227) soft = (size_t)v * 1024u; }
     }
+    const size_t soft = (size_t)tuning_value(FMLP_TUNE_SIM_SMEM_BUDGET_KB, "FMLP_SIM_SMEM_KB", 64, 227, 200) * 1024u;
     size_t budget = soft;
     int S = max_stages;
     auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + ((size_t)Cfg::W * s + 2) * sizeof(uint64_t); };   // ring barriers + the table barrier
     while (S > 2 && smem_of(S) > budget) --S;
-    const size_t smem = smem_of(S);
+    size_t smem = smem_of(S);
     if (smem > hard) return FMLP_ERR_UNSUPPORTED;
+    // tuning knob: request (not use) this many KB, so that no CTA of a concurrent kernel shares the SM
+    const int request_kb = tuning_value(FMLP_TUNE_SIM_REQUEST_SMEM_KB, "FMLP_SIM_REQUEST_SMEM_KB", 0, 227, 0);
+    if ((size_t)request_kb * 1024u > smem) smem = (size_t)request_kb * 1024u;
     a.S = S;
     auto kern = tag_sim_kernel<NPAIR, FOLD>;
     static size_t configured = 0;  // per template instance

@@ -89,6 +89,8 @@ class ClientShard:
 
     # traindata_idx bookkeeping costs two small device copies per round; benchmarks switch it off
     keep_history = True
+    # shared-memory pad (KB) of the prototype CTAs in the single-GPU two-stream round, None = leave the knob alone
+    proto_pad_smem_kb = 40
 
     def __init__(self, sizes, n_classes, active_classes, device=None, clean_frac=0.005, noise_frac=0.01,
                  L=0.3, U=0.7, sim_mode="folded", dataset_idx=None):
@@ -287,7 +289,23 @@ class ClientShard:
             elif side_stream is not None:
                 side_stream.wait_stream(stream)
                 with torch.cuda.stream(side_stream):
+                    # Single-GPU two-stream round: the prototype pass runs next to the similarity kernel.  Its CTAs
+                    # request 40 KB of (unused) shared memory each, so that at most one of them shares an SM with a
+                    # similarity CTA (measured: round 0.131 -> 0.124 ms, profiles/r02_exp_coresidency.txt).
+                    pad_prev = None
+                    if tail_stream is not None and self.proto_pad_smem_kb is not None:
+                        pad_prev = lib.fmlp_get_tuning(cabi.TUNE_PROTO_PAD_SMEM_KB)
+                        if pad_prev < 0:      # an explicit setting (or the environment variable) wins
+                            import os
+                            if os.environ.get("FMLP_PROTO_PAD_SMEM_KB") is None:
+                                lib.fmlp_set_tuning(cabi.TUNE_PROTO_PAD_SMEM_KB, int(self.proto_pad_smem_kb))
+                            else:
+                                pad_prev = None
+                        else:
+                            pad_prev = None
                     proto_stage(side_stream)
+                    if pad_prev is not None:
+                        lib.fmlp_set_tuning(cabi.TUNE_PROTO_PAD_SMEM_KB, pad_prev)
                     if aggregate_fn is None and tail_stream is not None:
                         # the small tails only need the prototypes: they leave the chain here and run next to the
                         # parameter aggregation instead of behind it (latency-bound, 7 us at the end of the round)

@@ -55,6 +55,22 @@ int fmlp_sm_count(void);
 /* Kernel launches issued by this library since it was loaded (process-wide, monotonic). */
 unsigned long long fmlp_launch_count(void);
 
+/* Scheduling knobs for rounds that run several of these kernels concurrently on different streams (process-wide;
+ * value -1 = unset: the environment variable of the same meaning, then the built-in default, applies).
+ *   FMLP_TUNE_PROTO_PAD_SMEM_KB   unused dynamic shared memory requested per prototype-accumulate CTA (0..56 KB):
+ *                                 limits how many of them share an SM with a CTA of the similarity kernel.  Measured
+ *                                 on B200 (profiles/r02_exp_coresidency.txt): 40 KB -> at most one next to a
+ *                                 similarity CTA, round 0.131 -> 0.124 ms at BASELINE configs[1].   env FMLP_PROTO_PAD_SMEM_KB
+ *   FMLP_TUNE_SIM_REQUEST_SMEM_KB the similarity kernel requests at least this much shared memory per CTA (0..227).
+ *                                 env FMLP_SIM_REQUEST_SMEM_KB
+ *   FMLP_TUNE_SIM_SMEM_BUDGET_KB  shared memory the similarity kernel's ring may use (64..227, default 200). env FMLP_SIM_SMEM_KB */
+#define FMLP_TUNE_PROTO_PAD_SMEM_KB 0
+#define FMLP_TUNE_SIM_REQUEST_SMEM_KB 1
+#define FMLP_TUNE_SIM_SMEM_BUDGET_KB 2
+#define FMLP_TUNE_COUNT 3
+int fmlp_set_tuning(int knob, int value);
+int fmlp_get_tuning(int knob);
+
 /* ------------------------------------------------------------------ K1: FedAvg
  * Replaces utils/FedAvg.py:7-14 `FedAvg` (and its twin `Fed_w` :16-23):
  *     out[j] = ((((w_0[j]*n_0) + w_1[j]*n_1) + ...) + w_{K-1}[j]*n_{K-1}) / sum(n)

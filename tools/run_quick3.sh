@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q -k "proto or round or flow or local_update" ) > gpurun_out/pytest_quick.log 2>&1
-tail -2 gpurun_out/pytest_quick.log
-for v in "FMLP_PROTO_TMA=1 FMLP_PROTO_CTAS=1" "FMLP_PROTO_TMA=1 FMLP_PROTO_CTAS=2" "FMLP_PROTO_TMA=0"; do
-( env $v timeout 600 python bench.py --skip-e2e --skip-cpu-baseline --steps 200 ) > gpurun_out/bench_q.json 2>> gpurun_out/bench_quick.err
-echo "--- $v"; python tools/show_bench.py gpurun_out/bench_q.json | grep "proto \|ms_per_step"
-done
+for rep in 1 2; do
+for v in "FMLP_SIM_REQUEST_SMEM_KB=227 FMLP_PROTO_PAD_SMEM_KB=0" "FMLP_SIM_REQUEST_SMEM_KB=227 FMLP_PROTO_PAD_SMEM_KB=40" "FMLP_SIM_REQUEST_SMEM_KB=200 FMLP_PROTO_PAD_SMEM_KB=40" "FMLP_SIM_REQUEST_SMEM_KB=0 FMLP_PROTO_PAD_SMEM_KB=48" "FMLP_SIM_REQUEST_SMEM_KB=0 FMLP_PROTO_PAD_SMEM_KB=56"; do
+( env $v timeout 600 python bench.py --skip-e2e --skip-cpu-baseline --steps 300 ) > gpurun_out/bench_q.json 2>> gpurun_out/bench_quick.err
+echo "--- rep $rep $v: $(python tools/show_bench.py gpurun_out/bench_q.json | grep ms_per_step | sed 's/value.*//' | tr '\n' ' ')"
+done; done
 tail -3 gpurun_out/bench_quick.err
