@@ -15,7 +15,7 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("FEDMLP_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"))
 
 ABI_VERSION = 3
-TUNE_PROTO_PAD_SMEM_KB, TUNE_SIM_REQUEST_SMEM_KB, TUNE_SIM_SMEM_BUDGET_KB = 0, 1, 2
+TUNE_PROTO_PAD_SMEM_KB, TUNE_SIM_REQUEST_SMEM_KB, TUNE_SIM_SMEM_BUDGET_KB, TUNE_SELECT_CLUSTER = 0, 1, 2, 3
 MAX_CLASSES = 32
 MAX_SEGMENTS = 64
 MAX_CLIENTS = 64

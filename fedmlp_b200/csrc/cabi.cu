@@ -3,7 +3,7 @@
 
 namespace fmlp {
 unsigned long long g_launch_count = 0;
-int g_tuning[FMLP_TUNE_COUNT] = {-1, -1, -1};     // -1 = not set: the environment variable / built-in default applies
+int g_tuning[FMLP_TUNE_COUNT] = {-1, -1, -1, -1};     // -1 = not set: the environment variable / built-in default applies
 }
 
 extern "C" unsigned long long fmlp_launch_count(void) { return __atomic_load_n(&fmlp::g_launch_count, __ATOMIC_RELAXED); }

@@ -13,12 +13,19 @@
 // order of equal elements) and min_n_indices.  All comps of an item are distinct, so the
 // selection "comp >= T" has exactly m (resp. k) members.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace fmlp {
 
 constexpr int kSelBins = 2048;  // 11-bit digits
+// Histogram copies per CTA (indexed by lane & 7).  The leading digit of |sim| (exponent + 3 mantissa bits) takes only
+// a few dozen values, so with one copy the 32 lanes of a warp serialised on a handful of shared-memory words in the
+// first sweep (r02: ~1 cycle per KEY); the kernel owns its SM anyway (1024 threads), so it spends 128 KB on eight
+// copies and adds them up when the bins are scanned.
+constexpr int kSelCopies = 8;
+constexpr size_t kSelSmemBytes = (size_t)kSelCopies * 2 * kSelBins * sizeof(int);
 
 struct SelArgs {
     const float* sim;
@@ -72,37 +79,73 @@ __device__ __forceinline__ unsigned long long make_comp(float s, uint32_t local_
 // side: 0 clean (sim >= 0), 1 noise (sim < 0), -1 neither (NaN) — np.where(sim >= 0) / (sim < 0)
 __device__ __forceinline__ int side_of(float s) { return s >= 0.f ? 0 : (s < 0.f ? 1 : -1); }
 
-// IPT > 0: every thread keeps its IPT candidate keys in registers for all passes (segments of up
+// ---- thread-block cluster helpers (an item may be split over the CTAs of one cluster) -----------
+__device__ __forceinline__ uint32_t sel_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t sel_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void sel_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory object of this CTA) in the CTA of rank `rank` of the cluster
+__device__ __forceinline__ uint32_t sel_dsmem(const void* p, uint32_t rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ int sel_dsmem_ld(uint32_t addr) { int v; asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long sel_dsmem_ld64(uint32_t addr) { unsigned long long v; asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void sel_dsmem_st64(uint32_t addr, unsigned long long v) { asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ int sel_dsmem_add(uint32_t addr, int v) { int o; asm volatile("atom.shared::cluster.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); return o; }
+
+// An item (segment, class) is handled by ONE CLUSTER of `cs` CTAs (cs = 1: a plain CTA).  CTA `cr` of the cluster
+// owns rows [cr*chunk, (cr+1)*chunk) of the segment; the per-pass histograms are built per CTA and added up by every
+// CTA through distributed shared memory, the small-bin gather list, the selection counters and the thresholds
+// live in the shared memory of CTA 0.  r02: one CTA per item left 13 CTAs on 148 SMs for the single-client
+// 85,000-row workload (84 us, issue-bound on those 13 SMs: ~190 instructions per key over its sweeps).
+// IPT > 0: every thread keeps its IPT candidate keys in registers for all passes (CTA chunks of up
 // to IPT * THREADS rows); IPT == 0: keys are re-read from global memory in every pass.
 // key = comp | side << 63.  Both sides share every histogram pass and every scan.
-template <int IPT, int THREADS>
+// COPIES: histogram copies (1 or kSelCopies); RESOLVE: leave the digit loop for the small-bin gather.  Items of up to
+// 16,384 rows run as before (one CTA, keys in registers, one 16 KB histogram, six cheap digit sweeps): for them the
+// extra shared memory and the gather sweep cost more than they save (r02: 12.4 -> 16.4 us at 8 x 6,875 rows).
+template <int IPT, int THREADS, int COPIES, bool RESOLVE>
 __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_constant__ SelArgs a) {
     constexpr bool CACHED = IPT > 0;
     constexpr int NK = CACHED ? IPT : 1;
     constexpr int BPT = kSelBins / THREADS;  // bins per thread in the scan (2 or 4)
-    __shared__ int s_hist[2][kSelBins];      // reused as the rank staging tile (2048 x u64)
+    extern __shared__ __align__(16) int s_hist_all[];   // [COPIES][2][kSelBins]; copy 0 doubles as the merged
+    int (*s_hist)[kSelBins] = reinterpret_cast<int (*)[kSelBins]>(s_hist_all);   // histogram / gather list / rank tile
     __shared__ unsigned long long s_warp[THREADS / 32 + 1];
     __shared__ int s_found[2][3];            // per side: bin, remaining-in-bin, bin count
-    __shared__ int s_count[3];               // selected per side, candidates seen
+    __shared__ int s_count[3];               // selected per side, candidates seen (cluster: those of CTA 0 count)
+    __shared__ int s_gather[2];              // small-bin gather: keys appended per side (CTA 0's)
+    __shared__ unsigned long long s_thresh[2];
 
     // chained to the similarity kernel (and the fill+loss kernel to this one) by programmatic dependent launches:
     // the launch latency of each hides behind its predecessor; the data dependency is the wait below
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int item = blockIdx.x;
+    const uint32_t cs = sel_cluster_size(), cr = sel_cluster_rank();
+    const int item = blockIdx.x / cs;
     const int s = item / a.C, c = item - s * a.C;
     int32_t* counts = a.counts + (int64_t)item * 4;
-    if (!((a.seg.mask_a[s] >> c) & 1u)) {
-        if (threadIdx.x < 4) counts[threadIdx.x] = 0;
-        if (threadIdx.x == 0 && a.remaining) a.remaining[item] = 0;
+    if (!((a.seg.mask_a[s] >> c) & 1u)) {       // uniform over the cluster
+        if (cr == 0) {
+            if (threadIdx.x < 4) counts[threadIdx.x] = 0;
+            if (threadIdx.x == 0 && a.remaining) a.remaining[item] = 0;
+        }
         return;
     }
     const int64_t r0 = a.seg.rows[s];
-    const uint32_t n = (uint32_t)(a.seg.rows[s + 1] - r0);
+    const uint32_t n_seg = (uint32_t)(a.seg.rows[s + 1] - r0);
+    const uint32_t chunk = (n_seg + cs - 1) / cs;
+    const uint32_t lo = min(n_seg, cr * chunk);           // this CTA's rows of the segment: [lo, n)
+    const uint32_t n = min(n_seg, lo + chunk);
     const float* sim = a.sim + (int64_t)c * a.ld_sim + r0;
     uint8_t* tag = a.tag + (int64_t)c * a.ld_tag + r0;
     constexpr unsigned long long kSideBit = 1ull << 63;
     if (threadIdx.x < 3) s_count[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_gather[threadIdx.x] = 0;
 
     // ---- candidate keys ------------------------------------------------------------------
     unsigned long long key[NK];
@@ -113,14 +156,14 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
         uint8_t tg[NK];
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            const uint32_t i = (uint32_t)k * THREADS + threadIdx.x;
+            const uint32_t i = lo + (uint32_t)k * THREADS + threadIdx.x;
             const bool in = i < n;
             tg[k] = in ? tag[i] : (uint8_t)1;
             v[k] = in ? sim[i] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            const uint32_t i = (uint32_t)k * THREADS + threadIdx.x;
+            const uint32_t i = lo + (uint32_t)k * THREADS + threadIdx.x;
             const int sd = side_of(v[k]);
             key[k] = make_comp(v[k], i) | (sd == 1 ? kSideBit : 0ull);
             if (tg[k] == 0) { ++n_cand; if (sd >= 0) valid |= 1u << k; }
@@ -138,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
             // over an 85,000-row client was ~80 serial L2 round trips per thread (r02: 136 us for 13 classes;
             // 84 us with batches of 8, eight sweeps per item)
             constexpr int U = 16;
-            for (uint32_t base0 = 0; base0 < n; base0 += THREADS * U) {      // same trip count for every thread
+            for (uint32_t base0 = lo; base0 < n; base0 += THREADS * U) {     // same trip count for every thread
                 const uint32_t base = base0 + threadIdx.x;
                 uint8_t tg[U];
                 float v[U];
@@ -177,7 +220,8 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
         if (done[0] && done[1]) break;
         const int shift = pass < 5 ? 52 - 11 * pass : 0;
         const int width = pass < 5 ? 11 : 8;
-        for (int i = threadIdx.x; i < 2 * kSelBins; i += THREADS) (&s_hist[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < COPIES * 2 * kSelBins / 4; i += THREADS)
+            reinterpret_cast<int4*>(s_hist_all)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
         const unsigned long long dmask = (1ull << width) - 1ull;
         const unsigned long long pre0 = prefix[0], pre1 = prefix[1];
@@ -186,19 +230,42 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
             const int sd = (int)(k >> 63);
             const unsigned long long comp = k & ~kSideBit;
             const bool hit = ok && !(sd ? d1 : d0) && (pass == 0 || (comp >> (shift + width)) == (sd ? pre1 : pre0));
-            if (hit) atomicAdd(&s_hist[sd][(int)((comp >> shift) & dmask)], 1);
+            if (hit) atomicAdd(&s_hist_all[((threadIdx.x & (COPIES - 1)) * 2 + sd) * kSelBins + (int)((comp >> shift) & dmask)], 1);
         }, !CACHED && pass == 0);
         __syncthreads();
-        // bins are visited from the top: thread t owns bins 2047-BPT*t .. 2047-BPT*t-(BPT-1)
+        // bins are visited from the top: thread t owns bins 2047-BPT*t .. 2047-BPT*t-(BPT-1); it adds up the copies
         int h[2][BPT];
         unsigned long long ls = 0ull;
 #pragma unroll
         for (int j = 0; j < BPT; ++j) {
             const int b = kSelBins - 1 - (BPT * (int)threadIdx.x + j);
-            h[0][j] = s_hist[0][b];
-            h[1][j] = s_hist[1][b];
-            ls += (unsigned long long)(uint32_t)h[0][j] | ((unsigned long long)(uint32_t)h[1][j] << 32);
+            int v0 = 0, v1 = 0;
+#pragma unroll
+            for (int cp = 0; cp < COPIES; ++cp) {
+                v0 += s_hist_all[(cp * 2 + 0) * kSelBins + b];
+                v1 += s_hist_all[(cp * 2 + 1) * kSelBins + b];
+            }
+            h[0][j] = v0; h[1][j] = v1;
+            if (cs > 1) { s_hist[0][b] = v0; s_hist[1][b] = v1; }    // copy 0 := this CTA's histogram (own bins only)
         }
+        if (cs > 1) {
+            sel_cluster_sync();                                   // every CTA's histogram is complete
+            // the item's histogram = sum of the cluster's histograms, read through distributed shared memory
+            // (all loads independent; every CTA computes the same sums and therefore takes the same decisions)
+            for (uint32_t r = 1; r < cs; ++r) {
+                const uint32_t rr = (cr + r) % cs;                // start at the neighbour: spreads the remote reads
+#pragma unroll
+                for (int j = 0; j < BPT; ++j) {
+                    const int b = kSelBins - 1 - (BPT * (int)threadIdx.x + j);
+                    h[0][j] += sel_dsmem_ld(sel_dsmem(&s_hist[0][b], rr));
+                    h[1][j] += sel_dsmem_ld(sel_dsmem(&s_hist[1][b], rr));
+                }
+            }
+            sel_cluster_sync();                                   // all reads done: the histograms may be reused
+        }
+#pragma unroll
+        for (int j = 0; j < BPT; ++j)
+            ls += (unsigned long long)(uint32_t)h[0][j] | ((unsigned long long)(uint32_t)h[1][j] << 32);
         unsigned long long total2;
         const unsigned long long ex2 = block_exclusive_scan2<THREADS>(ls, s_warp, &total2);
 #pragma unroll
@@ -241,17 +308,16 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
                 done[sd] = true;
             } else {
                 rem[sd] = rem_in;
-                if (bin_count <= kSmallBin && shift > 0) { resolve[sd] = true; res_shift[sd] = shift; done[sd] = true; }
+                if (RESOLVE && bin_count <= kSmallBin && shift > 0) { resolve[sd] = true; res_shift[sd] = shift; done[sd] = true; }
             }
         }
         __syncthreads();
     }
 
     // ---- small target bins: gather the keys that share the prefix, take the rem-th largest ----
-    if (resolve[0] || resolve[1]) {          // uniform across the CTA
-        unsigned long long* list = reinterpret_cast<unsigned long long*>(&s_hist[0][0]);   // [2][kSmallBin], histogram is dead
-        if (threadIdx.x < 2) s_found[threadIdx.x][0] = 0;
-        __syncthreads();
+    if (RESOLVE && (resolve[0] || resolve[1])) {          // uniform across the cluster
+        unsigned long long* list = reinterpret_cast<unsigned long long*>(&s_hist[0][0]);   // [2][kSmallBin] in CTA 0, histogram is dead
+        const uint32_t list0 = sel_dsmem(list, 0), gather0 = sel_dsmem(&s_gather[0], 0);
         const unsigned long long pre0 = prefix[0], pre1 = prefix[1];
         const int sh0 = res_shift[0], sh1 = res_shift[1];
         const bool rs0 = resolve[0], rs1 = resolve[1];
@@ -260,57 +326,70 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
             const unsigned long long comp = k & ~kSideBit;
             if (!ok || !(sd ? rs1 : rs0)) return;
             if ((comp >> (sd ? sh1 : sh0)) == (sd ? pre1 : pre0)) {
-                const int slot = atomicAdd(&s_found[sd][0], 1);
-                if (slot < kSmallBin) list[sd * kSmallBin + slot] = comp;
+                if (cs > 1) {
+                    const int slot = sel_dsmem_add(gather0 + 4u * sd, 1);
+                    if (slot < kSmallBin) sel_dsmem_st64(list0 + 8u * (uint32_t)(sd * kSmallBin + slot), comp);
+                } else {
+                    const int slot = atomicAdd(&s_gather[sd], 1);
+                    if (slot < kSmallBin) list[sd * kSmallBin + slot] = comp;
+                }
             }
         });
-        __syncthreads();
+        if (cs > 1) sel_cluster_sync(); else __syncthreads();
+        if (cr == 0) {
 #pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            if (!resolve[sd]) continue;
-            const int cnt = min(s_found[sd][0], kSmallBin);
-            __syncthreads();
-            if ((int)threadIdx.x < cnt) {
-                const unsigned long long mine = list[sd * kSmallBin + threadIdx.x];
-                int rank = 0;
-                for (int j = 0; j < cnt; ++j) rank += (list[sd * kSmallBin + j] > mine) ? 1 : 0;
-                if (rank == rem[sd] - 1) *reinterpret_cast<unsigned long long*>(&s_warp[sd]) = mine;
+            for (int sd = 0; sd < 2; ++sd) {
+                if (!resolve[sd]) continue;
+                const int cnt = min(s_gather[sd], kSmallBin);
+                if ((int)threadIdx.x < cnt) {
+                    const unsigned long long mine = list[sd * kSmallBin + threadIdx.x];
+                    int rank = 0;
+                    for (int j = 0; j < cnt; ++j) rank += (list[sd * kSmallBin + j] > mine) ? 1 : 0;
+                    if (rank == rem[sd] - 1) s_thresh[sd] = mine;
+                }
             }
-            __syncthreads();
-            thresh[sd] = s_warp[sd];
         }
-        __syncthreads();
+        if (cs > 1) sel_cluster_sync(); else __syncthreads();
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd)
+            if (resolve[sd]) thresh[sd] = cs > 1 ? sel_dsmem_ld64(sel_dsmem(&s_thresh[sd], 0)) : s_thresh[sd];
     }
 
     // ---- compaction: mark the tag state and collect the selected comps -------------------
+    const uint32_t count0 = sel_dsmem(&s_count[0], 0);
     n_cand = warp_sum_i(n_cand);
-    if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(&s_count[2], n_cand);
+    if ((threadIdx.x & 31) == 0 && n_cand) {
+        if (cs > 1) sel_dsmem_add(count0 + 8u, n_cand); else atomicAdd(&s_count[2], n_cand);
+    }
     {
         const unsigned long long t0 = thresh[0], t1 = thresh[1];
         for_each([&](unsigned long long k, bool ok) {
             const int sd = (int)(k >> 63);
             const unsigned long long comp = k & ~kSideBit;
             if (ok && comp >= (sd ? t1 : t0)) {
-                const int slot = atomicAdd(&s_count[sd], 1);
+                const int slot = cs > 1 ? sel_dsmem_add(count0 + 4u * sd, 1) : atomicAdd(&s_count[sd], 1);
                 if (slot < a.cap) a.cand[((int64_t)item * 2 + sd) * a.cap + slot] = comp;
                 tag[0xFFFFFFFFu - (uint32_t)(comp & 0xFFFFFFFFull)] = (uint8_t)(1 + sd);
             }
         });
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (cs > 1) sel_cluster_sync(); else __syncthreads();     // counters final; the cluster's a.cand writes are visible
+    int total_sel[2];
+    total_sel[0] = cs > 1 ? sel_dsmem_ld(count0) : s_count[0];
+    total_sel[1] = cs > 1 ? sel_dsmem_ld(count0 + 4u) : s_count[1];
+    if (threadIdx.x == 0 && cr == 0) {
         counts[0] = n_side[0]; counts[1] = n_side[1]; counts[2] = want[0]; counts[3] = want[1];
         if (a.remaining) a.remaining[item] = s_count[2] - s_count[0] - s_count[1];
     }
 
-    // ---- rank order: position = number of selected comps that are larger -----------------
+    // ---- rank order: position = number of selected comps that are larger (CTA cr ranks every cs-th batch) ----
     unsigned long long* tile = reinterpret_cast<unsigned long long*>(&s_hist[0][0]);  // 2048 entries
     constexpr int kTile = 2048;
     for (int sd = 0; sd < 2; ++sd) {
-        const int cnt = (int)min((int64_t)s_count[sd], a.cap);
+        const int cnt = (int)min((int64_t)total_sel[sd], a.cap);
         const unsigned long long* cand = a.cand + ((int64_t)item * 2 + sd) * a.cap;
         int32_t* out = a.sel + ((int64_t)item * 2 + sd) * a.cap;
-        for (int e0 = 0; e0 < cnt; e0 += THREADS) {
+        for (int e0 = (int)cr * THREADS; e0 < cnt; e0 += (int)cs * THREADS) {
             const int e = e0 + threadIdx.x;
             const unsigned long long mine = e < cnt ? cand[e] : 0ull;
             int rank = 0;
@@ -326,6 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1) tag_select_kernel(const __grid_con
         }
         __syncthreads();
     }
+    if (cs > 1) sel_cluster_sync();      // nobody leaves while its shared memory may still be read
 }
 
 struct FillArgs {
@@ -389,18 +469,43 @@ extern "C" int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, i
     a.C = C;
     int64_t max_rows = 0;
     for (int s = 0; s < S; ++s) max_rows = std::max<int64_t>(max_rows, seg_rows[s + 1] - seg_rows[s]);
-    const unsigned grid = (unsigned)(S * C);
+    // CTAs per item (one cluster): enough for the keys of the largest segment to stay in registers (16 x 1024 per CTA),
+    // and, when the launch is small, enough to put the items on more SMs (FMLP_SELECT_CLUSTER overrides: 1, 2, 4, 8)
+    int cs = 1;
+    while (cs < 8 && (max_rows + cs - 1) / cs > 16 * 1024) cs *= 2;
+    {
+        const int forced = tuning_value(FMLP_TUNE_SELECT_CLUSTER, "FMLP_SELECT_CLUSTER", 0, 8, 0);
+        if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cs = forced;
+    }
+    const int64_t per_cta = (max_rows + cs - 1) / cs;
+    const unsigned grid = (unsigned)(S * C * cs);
     cudaStream_t st = (cudaStream_t)stream;
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cs; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = cs > 1 ? 2 : 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(1024); cfg.stream = st;
+    const bool big = cs > 1 || per_cta > 16 * 1024;       // split or re-reading items: copies + small-bin gather
+    cfg.dynamicSmemBytes = big ? kSelSmemBytes : kSelSmemBytes / kSelCopies;
+    {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e0 = cudaFuncSetAttribute(tag_select_kernel<8, 1024, kSelCopies, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
+            if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(tag_select_kernel<16, 1024, kSelCopies, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
+            if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(tag_select_kernel<0, 1024, kSelCopies, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
+            if (e0 != cudaSuccess) return (int)e0;
+            configured = true;
+        }
+    }
     cudaError_t e;
-    if (max_rows <= 8 * 1024) e = cudaLaunchKernelEx(&cfg, tag_select_kernel<8, 1024>, a);
-    else if (max_rows <= 16 * 1024) e = cudaLaunchKernelEx(&cfg, tag_select_kernel<16, 1024>, a);
-    else e = cudaLaunchKernelEx(&cfg, tag_select_kernel<0, 1024>, a);
+    if (!big) e = per_cta <= 8 * 1024 ? cudaLaunchKernelEx(&cfg, tag_select_kernel<8, 1024, 1, false>, a)
+                                      : cudaLaunchKernelEx(&cfg, tag_select_kernel<16, 1024, 1, false>, a);
+    else if (per_cta <= 8 * 1024) e = cudaLaunchKernelEx(&cfg, tag_select_kernel<8, 1024, kSelCopies, true>, a);
+    else if (per_cta <= 16 * 1024) e = cudaLaunchKernelEx(&cfg, tag_select_kernel<16, 1024, kSelCopies, true>, a);
+    else e = cudaLaunchKernelEx(&cfg, tag_select_kernel<0, 1024, kSelCopies, true>, a);
     return e == cudaSuccess ? launch_status() : (int)e;
 }
 

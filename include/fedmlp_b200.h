@@ -63,11 +63,14 @@ unsigned long long fmlp_launch_count(void);
  *                                 similarity CTA, round 0.131 -> 0.124 ms at BASELINE configs[1].   env FMLP_PROTO_PAD_SMEM_KB
  *   FMLP_TUNE_SIM_REQUEST_SMEM_KB the similarity kernel requests at least this much shared memory per CTA (0..227).
  *                                 env FMLP_SIM_REQUEST_SMEM_KB
- *   FMLP_TUNE_SIM_SMEM_BUDGET_KB  shared memory the similarity kernel's ring may use (64..227, default 200). env FMLP_SIM_SMEM_KB */
+ *   FMLP_TUNE_SIM_SMEM_BUDGET_KB  shared memory the similarity kernel's ring may use (64..227, default 200). env FMLP_SIM_SMEM_KB
+ *   FMLP_TUNE_SELECT_CLUSTER      CTAs per (segment, class) item of the selection kernel: 1, 2, 4 or 8 (one thread-block
+ *                                 cluster per item); 0 / unset = as few as keep a CTA's keys in registers. env FMLP_SELECT_CLUSTER */
 #define FMLP_TUNE_PROTO_PAD_SMEM_KB 0
 #define FMLP_TUNE_SIM_REQUEST_SMEM_KB 1
 #define FMLP_TUNE_SIM_SMEM_BUDGET_KB 2
-#define FMLP_TUNE_COUNT 3
+#define FMLP_TUNE_SELECT_CLUSTER 3
+#define FMLP_TUNE_COUNT 4
 int fmlp_set_tuning(int knob, int value);
 int fmlp_get_tuning(int knob);
 

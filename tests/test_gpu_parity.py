@@ -211,8 +211,36 @@ def test_select_golden_sims(F):
             assert sel[0, c, 1, :n].tolist() == z[f"min/{c}/{n}"].tolist()
 
 
-@pytest.mark.parametrize("N,cf,nf", [(55000, 0.005, 0.01), (6875, 0.005, 0.01), (85000, 0.005, 0.01), (2000, 0.3, 0.6), (1000, 1.0, 1.0), (37, 0.0, 0.0)])
-def test_select_vs_oracle_random(F, N, cf, nf):
+@pytest.fixture
+def select_cluster(lib, request):
+    """Forces the number of CTAs (one thread-block cluster) per (client, class) item of the selection kernel."""
+    from fedmlp_b200 import _cabi as cabi
+    lib.fmlp_set_tuning(cabi.TUNE_SELECT_CLUSTER, request.param)
+    yield request.param
+    lib.fmlp_set_tuning(cabi.TUNE_SELECT_CLUSTER, -1)
+
+
+@pytest.mark.parametrize("select_cluster", [0, 2, 8], indirect=True)
+def test_select_ties_golden_clustered(F, select_cluster):
+    """The reference's tie order (utils/utils.py:24-35) when an item is split over the CTAs of a cluster."""
+    z = gu.load("tagging.npz")
+    vals = z["ties/vals"]
+    n_clean, n_noise = int(np.sum(vals >= 0)), int(np.sum(vals < 0))
+    for m in (0, 1, n_clean // 2, n_clean):
+        for k in (0, 1, n_noise // 2, n_noise):
+            cf, nf = min(1.0, (m + 0.5) / n_clean), min(1.0, (k + 0.5) / n_noise)
+            tb, counts, sel = _select_on(F, vals[None, :], [[0]], 1, cf, nf)
+            assert counts[0, 0].tolist() == [n_clean, n_noise, m, k]
+            assert sel[0, 0, 0, :m].tolist() == z[f"ties/max/{m}"].tolist()
+            assert sel[0, 0, 1, :k].tolist() == z[f"ties/min/{k}"].tolist()
+
+
+@pytest.mark.parametrize("select_cluster", [0, 2, 8], indirect=True)
+@pytest.mark.parametrize("N,cf,nf", [(55000, 0.005, 0.01), (6875, 0.005, 0.01), (85000, 0.005, 0.01), (2000, 0.3, 0.6), (1000, 1.0, 1.0), (37, 0.0, 0.0),
+                                     (150000, 0.005, 0.01)])
+def test_select_vs_oracle_random(F, N, cf, nf, select_cluster):
+    """select_cluster 0 = automatic (1 CTA up to 16,384 rows, then a cluster of 2 / 4 / 8; 150,000 rows: 8 CTAs that
+    re-read their keys), 2 / 8 = forced split."""
     rng = np.random.default_rng(N)
     C = 4
     sims = rng.normal(0, 0.02, size=(C, N)).astype(np.float32)

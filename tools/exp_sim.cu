@@ -11,7 +11,7 @@
 
 #include "fedmlp_b200.h"
 
-namespace fmlp { unsigned long long g_launch_count = 0; int g_tuning[FMLP_TUNE_COUNT] = {-1, -1, -1}; }
+namespace fmlp { unsigned long long g_launch_count = 0; int g_tuning[FMLP_TUNE_COUNT] = {-1, -1, -1, -1}; }
 #ifdef FMLP_SIM_TRACE
 extern "C" int fmlp_sim_trace_read(unsigned long long* host, int n);
 #endif
