@@ -142,6 +142,11 @@ __global__ void __launch_bounds__(256) sim_quad_table_kernel(const float* __rest
                                                              int npair, const __grid_constant__ SimArgs a,
                                                              float* __restrict__ table) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the main kernel may start its prologue now
+    // This kernel is itself launched as a programmatic dependent of whatever precedes it in the stream (its CTAs are
+    // resident and waiting when the predecessor drains: the 3-6 us launch chain in front of the main kernel shrinks to
+    // the table's own run time).  Everything it reads may be the predecessor's output, hence the wait first; the main
+    // kernel touches global memory only behind its own wait, which covers this kernel and, transitively, that one.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef FMLP_SIM_TRACE
     if (threadIdx.x == 0 && blockIdx.x == 0) g_sim_trace[160 * 8] = sim_gtime();
 #endif
@@ -441,9 +446,18 @@ static int launch_sim(SimArgs& a, const SimFeat& ft, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return FMLP_ERR_UNSUPPORTED;
     const int sms = sm_count();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
-    sim_quad_table_kernel<<<NPAIR, 256, 0, st>>>(a.proto, a.D, a.NG, FOLD ? 1 : 0, NPAIR, a, const_cast<float*>(a.table));
-    int rc = launch_status();
-    if (rc != FMLP_OK) return rc;
+    {
+        cudaLaunchConfig_t tcfg = {};
+        cudaLaunchAttribute tattr[1];
+        tattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        tattr[0].val.programmaticStreamSerializationAllowed = 1;
+        tcfg.attrs = tattr; tcfg.numAttrs = sim_use_pdl() ? 1 : 0;
+        tcfg.gridDim = dim3(NPAIR); tcfg.blockDim = dim3(256); tcfg.dynamicSmemBytes = 0; tcfg.stream = st;
+        cudaError_t te = cudaLaunchKernelEx(&tcfg, sim_quad_table_kernel, a.proto, a.D, a.NG, FOLD ? 1 : 0, NPAIR, a,
+                                            const_cast<float*>(a.table));
+        int rc = te == cudaSuccess ? launch_status() : (int)te;
+        if (rc != FMLP_OK) return rc;
+    }
     const int64_t n_tiles = (a.n_total + Cfg::ROWS - 1) / Cfg::ROWS;
     const int64_t blocks = n_tiles < sms ? n_tiles : sms;     // persistent: one CTA per SM, tiles round-robin
     // programmatic dependent launch: the main kernel's barrier setup and first feature boxes overlap

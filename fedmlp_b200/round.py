@@ -20,6 +20,7 @@ the hot path measured here.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -91,6 +92,10 @@ class ClientShard:
     keep_history = True
     # shared-memory pad (KB) of the prototype CTAs in the single-GPU two-stream round, None = leave the knob alone
     proto_pad_smem_kb = 40
+    # single-GPU two-stream round: "concurrent" = similarity and prototype kernels start together; "sim_first" /
+    # "proto_first" = one of the two streaming kernels runs alone and the other starts behind it (same work, same
+    # results; which is fastest depends on the shape: bench.py measures the three and keeps the best)
+    schedule = "concurrent"
 
     def __init__(self, sizes, n_classes, active_classes, device=None, clean_frac=0.005, noise_frac=0.01,
                  L=0.3, U=0.7, sim_mode="folded", dataset_idx=None):
@@ -271,6 +276,10 @@ class ClientShard:
                 {"sim": sim_stage, "proto": lambda: proto_stage(stream), "fedavg": lambda: aggregate_stage(stream),
                  "tail": select_fill_loss}[only]()
                 return RoundResult(pl.counts, pl.sel, pl.losses, pl.dz, protos, out["glob"], ev)
+            sim_launched = False
+            schedule = os.environ.get("FMLP_ROUND_SCHEDULE") or self.schedule
+            if schedule not in ("concurrent", "sim_first", "proto_first"):
+                raise ValueError(f"unknown round schedule {schedule!r}")
             tail_stream = None
             if side_stream is not None and agg_stream is None and aggregate_tails and tails_fn is None and aggregate_fn is None:
                 if self._tail_stream is None:
@@ -287,6 +296,11 @@ class ClientShard:
                     proto_stage(side_stream)
                     tails_stage(side_stream)
             elif side_stream is not None:
+                if schedule == "sim_first":
+                    # the similarity kernel runs alone; the prototype pass starts behind it, next to select / fill+loss
+                    sim_stage()
+                    mark("sim")
+                    sim_launched = True
                 side_stream.wait_stream(stream)
                 with torch.cuda.stream(side_stream):
                     # Single-GPU two-stream round: the prototype pass runs next to the similarity kernel.  Its CTAs
@@ -296,7 +310,6 @@ class ClientShard:
                     if tail_stream is not None and self.proto_pad_smem_kb is not None:
                         pad_prev = lib.fmlp_get_tuning(cabi.TUNE_PROTO_PAD_SMEM_KB)
                         if pad_prev < 0:      # an explicit setting (or the environment variable) wins
-                            import os
                             if os.environ.get("FMLP_PROTO_PAD_SMEM_KB") is None:
                                 lib.fmlp_set_tuning(cabi.TUNE_PROTO_PAD_SMEM_KB, int(self.proto_pad_smem_kb))
                             else:
@@ -306,6 +319,11 @@ class ClientShard:
                     proto_stage(side_stream)
                     if pad_prev is not None:
                         lib.fmlp_set_tuning(cabi.TUNE_PROTO_PAD_SMEM_KB, pad_prev)
+                    if schedule == "proto_first":
+                        # the prototype pass runs alone; the similarity kernel starts behind it, next to FedAvg
+                        proto_done = torch.cuda.Event()
+                        proto_done.record(side_stream)
+                        stream.wait_event(proto_done)
                     if aggregate_fn is None and tail_stream is not None:
                         # the small tails only need the prototypes: they leave the chain here and run next to the
                         # parameter aggregation instead of behind it (latency-bound, 7 us at the end of the round)
@@ -315,8 +333,9 @@ class ClientShard:
                         params_stage(side_stream)
                     else:
                         aggregate_stage(side_stream)
-            sim_stage()
-            mark("sim")
+            if not sim_launched:
+                sim_stage()
+                mark("sim")
             if side_stream is not None:
                 select_fill_loss()
                 stream.wait_stream(side_stream)

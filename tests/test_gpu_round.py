@@ -12,13 +12,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("two_streams", [False, True])
+@pytest.mark.parametrize("two_streams", [False, True, "sim_first", "proto_first"])
 @pytest.mark.parametrize("mode", ["pair", "folded"])
 def test_round_hot_path_matches_per_client_oracle(lib, mode, two_streams):
     """two_streams: the DAG form bench.py replays ({sim, select, fill+loss} || {prototypes, FedAvg} with the small
     aggregation tails forked off behind the prototype pass) must give the same results as the serial order."""
     from fedmlp_b200.round import ClientShard
     side = torch.cuda.Stream(device=DEV) if two_streams else None
+    schedule = two_streams if isinstance(two_streams, str) else "concurrent"   # ClientShard.schedule of the DAG form
 
     C, D, P = 5, 256, 10007 + 1          # P multiple of 4
     sizes = [700, 333, 1201, 64]
@@ -26,6 +27,7 @@ def test_round_hot_path_matches_per_client_oracle(lib, mode, two_streams):
     active = [[s % C] for s in range(S)]
     cf, nf = 0.03, 0.06
     shard = ClientShard(sizes, C, active, device=DEV, clean_frac=cf, noise_frac=nf, sim_mode=mode)
+    shard.schedule = schedule
     states = [O.TaggingState(list(range(n)), shard.missing[s]) for s, n in enumerate(sizes)]
     g = torch.Generator().manual_seed(11)
     flats = [torch.randn(P, generator=g) for _ in range(S)]
