@@ -32,6 +32,11 @@
 //     the table kernel is still running and only waits (griddepcontrol.wait) before the table copy.
 //     (First round-2 version: every CTA rebuilt the table in its prologue — 32..130 dependent L2 round
 //     trips per thread, 10..30 us in front of a 45..90 us kernel.)
+//   * The per-tile epilogue (add the W warps' partial sums, norms, reciprocal, segment lookup, store) belongs to
+//     TWO DEDICATED WARPS, one lane per row of the tile: the compute warps hand their partial sums over through
+//     shared memory and a full/empty mbarrier pair and go straight on with the next tile.  (r02 ncu source view at 14
+//     class vectors: 26 % of the kernel's samples sat in the epilogue, executed by all 8 compute warps between two
+//     block-wide barriers while no FMA was issued.)
 // Work per byte is (NV+1)/4 FMA with NV = 2M (pair mode) or M (FMLP_SIM_FOLDED: one dot against
 // q_c = P0/|P0| - P1/|P1|).  fp32 FFMA2 only: TF32/BF16 tensor cores would flip signs at 1e-3.
 #include <cuda.h>
@@ -71,6 +76,10 @@ struct SimArgs {
 #ifndef FMLP_SIM_TABLE_FIRST
 #define FMLP_SIM_TABLE_FIRST 1
 #endif
+// warps that do nothing but the per-tile epilogue (see the kernel); 2 x 32 lanes = one lane per row of a 64-row tile
+#ifndef FMLP_SIM_EPI_WARPS
+#define FMLP_SIM_EPI_WARPS 2
+#endif
 
 template <int NPAIR, bool FOLD>
 struct SimCfg {
@@ -80,7 +89,8 @@ struct SimCfg {
     static constexpr int W = (NV > 16 && FMLP_SIM_W > 4) ? 4 : FMLP_SIM_W;
     static constexpr int RT = (NV <= 8) ? FMLP_SIM_RT_SMALL : FMLP_SIM_RT_LARGE;  // rows per thread
     static constexpr int ROWS = 32 * RT;                                  // rows per tile
-    static constexpr int THREADS = 32 * W;
+    static constexpr int EW = FMLP_SIM_EPI_WARPS;                         // epilogue warps
+    static constexpr int THREADS = 32 * (W + EW);
     static constexpr int STAGE_BYTES = ROWS * 128;                        // one box: ROWS x 32 floats
     static constexpr int PV = NV + 1;                                     // partial values per row
 };
@@ -109,6 +119,9 @@ __device__ __forceinline__ void sim_mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void sim_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sim_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool sim_mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -198,7 +211,7 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
     float* sP = reinterpret_cast<float*>(sRing + (size_t)W * S * STAGE);   // [NG*8 column quads][NV] float4
     float* sPart = sP + (size_t)NG * 32 * NV;                              // [W][PV][ROWS] partial sums
     float* sNorm = sPart + (size_t)W * PV * ROWS;                          // [2*NPAIR] prototype norms, padded to 4
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sNorm + ((2 * NPAIR + 3) & ~3));   // [W][S] ring barriers, then 1 for the table
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sNorm + ((2 * NPAIR + 3) & ~3));   // [W][S] ring barriers, table, full, empty
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -207,9 +220,10 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int64_t n_tiles = (a.n_total + ROWS - 1) / ROWS;
-    const int my_groups = (NG > warp) ? (NG - warp + W - 1) / W : 0;       // column groups warp, warp+W, ...
-    const uint32_t ring_u32 = sim_smem_u32(sRing + (size_t)warp * S * STAGE);
-    const uint32_t bar_u32 = sim_smem_u32(sBar + warp * S);
+    const bool is_epi = warp >= W;                                         // epilogue warps: W .. W+EW-1
+    const int my_groups = (!is_epi && NG > warp) ? (NG - warp + W - 1) / W : 0;   // column groups warp, warp+W, ...
+    const uint32_t ring_u32 = sim_smem_u32(sRing + (size_t)(is_epi ? 0 : warp) * S * STAGE);
+    const uint32_t bar_u32 = sim_smem_u32(sBar + (is_epi ? 0 : warp) * S);
 
     // ---- producer state (lane 0 of each warp): next box = (tile, group) in consumption order
     int64_t p_tile = blockIdx.x;
@@ -225,9 +239,14 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
         p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
     };
     const uint32_t tbar_u32 = sim_smem_u32(sBar + W * S);
-    if (lane == 0) {
+    const uint32_t full_u32 = tbar_u32 + 8, empty_u32 = tbar_u32 + 16;    // partial sums ready / consumed
+    if (lane == 0 && !is_epi) {
         for (int s = 0; s < S; ++s) sim_mbar_init(bar_u32 + s * 8, 1);
-        if (warp == 0) sim_mbar_init(tbar_u32, 1);
+        if (warp == 0) {
+            sim_mbar_init(tbar_u32, 1);
+            sim_mbar_init(full_u32, W);                 // lane 0 of every compute warp
+            sim_mbar_init(empty_u32, Cfg::EW);          // lane 0 of every epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -246,10 +265,10 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
     // this grid's CTAs start, griddepcontrol.wait returns at once, so nothing is lost by waiting first.
     if (threadIdx.x == 0) load_table();
     __syncthreads();
-    if (lane == 0)
+    if (lane == 0 && !is_epi)
         for (int s = 0; s < S; ++s) issue();
 #else
-    if (lane == 0) {
+    if (lane == 0 && !is_epi) {
         for (int s = 0; s < S; ++s) issue();     // the ring fills while the table kernel finishes
         if (warp == 0) load_table();
     }
@@ -258,10 +277,59 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
     sim_mbar_wait(tbar_u32, 0);
     SIM_STAMP(1);
 
+    if (is_epi) {
+        // ---- epilogue warps: lane <-> row of the tile; reference op order (norm product, reciprocal, multiply, subtract)
+        const int et = threadIdx.x - 32 * W;
+        uint32_t ph = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            sim_mbar_wait(full_u32, ph);            // the W compute warps have stored this tile's partial sums
+            ph ^= 1u;
+            const int64_t row0 = tile * ROWS;
+            for (int r = et; r < ROWS; r += 32 * Cfg::EW) {
+                const int64_t row = row0 + r;
+                if (row >= a.n_total) continue;
+                const uint32_t mask = a.seg.mask_a[find_segment(a.seg.rows, a.seg.S, row)];
+                float ff = 0.f;
+#pragma unroll
+                for (int w = 0; w < W; ++w) ff += sPart[((size_t)w * PV + NV) * ROWS + r];     // fixed warp order: deterministic
+                const float nf = sqrtf(ff);
+                const float rnf = __frcp_rn(nf);
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    const int c = a.cls[q];
+                    if (!((mask >> c) & 1u)) continue;
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const float* part = sPart + (size_t)w * PV * ROWS + r;
+                        if (FOLD) {
+                            d0 += part[q * ROWS];
+                        } else {
+                            d0 += part[(2 * q) * ROWS];
+                            d1 += part[(2 * q + 1) * ROWS];
+                        }
+                    }
+                    float out;
+                    if (FOLD) {
+                        out = __fmul_rn(d0, rnf);
+                    } else {
+                        const float c0 = __fmul_rn(d0, __frcp_rn(__fmul_rn(nf, sNorm[2 * q])));
+                        const float c1 = __fmul_rn(d1, __frcp_rn(__fmul_rn(nf, sNorm[2 * q + 1])));
+                        out = __fsub_rn(c0, c1);
+                    }
+                    a.sim[(int64_t)c * a.ld_sim + row] = out;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) sim_mbar_arrive(empty_u32);      // the staging area may be overwritten
+        }
+        return;
+    }
+
     // lane's row inside a box: 128 bytes per row, 16-byte chunk k of row r sits at chunk k ^ (r & 7)
     const uint32_t row_off = (uint32_t)lane * 128u + ((uint32_t)(lane & 7) << 4);
     int slot = 0;
-    uint32_t parity = 0;
+    uint32_t parity = 0, eph = 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         u64 acc[RT][PV];
@@ -311,48 +379,14 @@ tag_sim_kernel(const __grid_constant__ SimArgs a, const __grid_constant__ CUtens
             if (++slot == S) { slot = 0; parity ^= 1u; }
         }
 
-        // ---- the W warps' partial sums meet in shared memory --------------------------------
-        __syncthreads();                        // the previous tile's epilogue reads are done
+        // ---- hand the partial sums to the epilogue warps and go on with the next tile -------------
+        if (tile != (int64_t)blockIdx.x) { sim_mbar_wait(empty_u32, eph); eph ^= 1u; }   // previous tile's sums consumed
 #pragma unroll
         for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int j = 0; j < PV; ++j) sPart[(warp * PV + j) * ROWS + r * 32 + lane] = pair_sum(acc[r][j]);
-        __syncthreads();
-
-        // ---- epilogue: thread -> (row, class subset); reference op order -------------------
-        const int64_t row0 = tile * ROWS;
-        for (int e = threadIdx.x; e < ROWS * NPAIR; e += Cfg::THREADS) {
-            const int q = e / ROWS, r = e - q * ROWS;
-            const int64_t row = row0 + r;
-            if (row < a.n_total) {
-                const int c = a.cls[q];
-                const int s = find_segment(a.seg.rows, a.seg.S, row);
-                if ((a.seg.mask_a[s] >> c) & 1u) {
-                    float ff = 0.f, d0 = 0.f, d1 = 0.f;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {            // fixed warp order: deterministic
-                        const float* part = sPart + (size_t)w * PV * ROWS + r;
-                        ff += part[NV * ROWS];
-                        if (FOLD) {
-                            d0 += part[q * ROWS];
-                        } else {
-                            d0 += part[(2 * q) * ROWS];
-                            d1 += part[(2 * q + 1) * ROWS];
-                        }
-                    }
-                    const float nf = sqrtf(ff);
-                    float out;
-                    if (FOLD) {
-                        out = __fmul_rn(d0, __frcp_rn(nf));
-                    } else {
-                        const float c0 = __fmul_rn(d0, __frcp_rn(__fmul_rn(nf, sNorm[2 * q])));
-                        const float c1 = __fmul_rn(d1, __frcp_rn(__fmul_rn(nf, sNorm[2 * q + 1])));
-                        out = __fsub_rn(c0, c1);
-                    }
-                    a.sim[(int64_t)c * a.ld_sim + row] = out;
-                }
-            }
-        }
+        __syncwarp();
+        if (lane == 0) sim_mbar_arrive(full_u32);
 #ifdef FMLP_SIM_TRACE
         if (tile == blockIdx.x) SIM_STAMP(2);
 #endif
@@ -393,7 +427,7 @@ static size_t sim_smem_min(int npair, bool fold, int NG) {
     const int RT = (nv <= 8) ? FMLP_SIM_RT_SMALL : FMLP_SIM_RT_LARGE;
     const size_t rows = 32 * RT;
     const size_t fixed = ((size_t)NG * 32 * nv + (size_t)W * (nv + 1) * rows + ((2 * npair + 3) & ~3)) * sizeof(float);
-    return (size_t)W * 2 * rows * 128 + fixed + ((size_t)W * 2 + 2) * sizeof(uint64_t);
+    return (size_t)W * 2 * rows * 128 + fixed + ((size_t)W * 2 + 4) * sizeof(uint64_t);
 }
 
 struct SimFeat {
@@ -417,7 +451,7 @@ static int launch_sim(SimArgs& a, const SimFeat& ft, cudaStream_t st) {
     const size_t soft = (size_t)tuning_value(FMLP_TUNE_SIM_SMEM_BUDGET_KB, "FMLP_SIM_SMEM_KB", 64, 227, 200) * 1024u;
     size_t budget = soft;
     int S = max_stages;
-    auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + ((size_t)Cfg::W * s + 2) * sizeof(uint64_t); };   // ring barriers + the table barrier
+    auto smem_of = [&](int s) { return (size_t)Cfg::W * s * Cfg::STAGE_BYTES + fixed + ((size_t)Cfg::W * s + 4) * sizeof(uint64_t); };   // ring barriers + table / full / empty
     while (S > 2 && smem_of(S) > budget) --S;
     size_t smem = smem_of(S);
     if (smem > hard) return FMLP_ERR_UNSUPPORTED;
