@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(512, NA == 1 ? 2 : 1) proto_accum_kernel(const
     }
 }
 
+constexpr int kFinGroups = 16, kFinCols = 16;   // finalize CTA: 16 slot groups x 16 float4 columns
+
 struct ProtoFinArgs {
     const float* partial;
     const int32_t* pcount;
@@ -201,89 +203,109 @@ struct ProtoFinArgs {
     int D, C, NA, guard_empty, first_pass, has_t;
 };
 
-// grid = (S * 2C, ceil(D / 256)), 256 threads = 4 slot groups x 64 float4 columns.  Row 2c+y of
-// segment s: the slot partials are added in a FIXED order (group g takes slots g, g+4, ... with
-// 4 loads in flight, then the four group sums are added in group order) -> deterministic, and
+// grid.y = ceil(D / 64), 256 threads = 16 slot groups x 16 float4 columns.  Row 2c+y of
+// segment s: the slot partials are added in a FIXED order (group g takes slots g, g+16, ... with
+// 4 loads in flight, then the sixteen group sums are added in group order) -> deterministic, and
 // the L2 round trips overlap instead of forming one 70-deep dependent chain (r01 ncu: 33 us).
+// Round 2: 16 groups x 64 columns per CTA instead of 4 x 256 — a single client of 85,000 rows has ~440 slots
+// and only 2 rows x D/256 CTAs with work, each walking 111 slots per group (~28 dependent batches).
 // Then the row is divided by its count (tensor / python int -> fp32 divide, :997-999,1241-1248).
+// grid.x = S * NA * 2: CTA (s, k, y) owns row 2c+y of segment s, c = the k-th class of this pass that is active on
+// the segment (it leaves at once when the segment has fewer) — only rows with work get CTAs (a grid over all 2C rows
+// launched 3,584 CTAs at C = 14, 16 of every 224 with anything to add).  The rows that stay zero, their counts and the
+// t counts are the job of the (s, 0, 0) CTAs of column block 0.
 __global__ void __launch_bounds__(256) proto_finalize_kernel(const __grid_constant__ ProtoFinArgs a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");                // slot partials of the accumulate kernel
     __shared__ int s_n[8];
-    __shared__ float4 s_part[4][64];
-    const int s = blockIdx.x / (2 * a.C);
-    const int row = blockIdx.x - s * 2 * a.C;
-    const int c = row >> 1, y = row & 1;
-    const int grp = threadIdx.x >> 6;                              // slot group 0..3
-    const int d = (blockIdx.y * 64 + (threadIdx.x & 63)) * 4;      // first of this thread's 4 columns
+    __shared__ float4 s_part[kFinGroups][kFinCols];
+    const int per_seg = 2 * a.NA;
+    const int s = blockIdx.x / per_seg;
+    const int ky = blockIdx.x - s * per_seg;
+    const int slot_i = ky >> 1, y = ky & 1;                        // position among this pass's classes, label value
+    const int grp = threadIdx.x / kFinCols;                        // slot group 0..kFinGroups-1
+    const int cw = threadIdx.x % kFinCols;
+    const int d = (blockIdx.y * kFinCols + cw) * 4;                // first of this thread's 4 columns
     const int64_t seg_lo = a.seg.rows[s], seg_hi = a.seg.rows[s + 1];
     const bool nonempty = seg_hi > seg_lo;
     const int64_t b0 = nonempty ? seg_lo / a.rows_per_cta : 0;
     const int64_t b1 = nonempty ? (seg_hi - 1) / a.rows_per_cta : -1;
     const uint32_t pass_active = a.seg.mask_a[s];
-    const bool mine = (pass_active >> c) & 1u;
-    const bool active_any = (a.seg.mask_b[s] >> c) & 1u;
 
-    // t counts: rows 0..C-1 of the first pass double as "class row" (one warp adds the slots)
-    if (a.first_pass && a.tcnt != nullptr && blockIdx.y == 0 && row < a.C && threadIdx.x < 32) {
-        int t = 0;
-        if (a.has_t)
-            for (int64_t b = b0 + threadIdx.x; b <= b1; b += 32)
-                t += a.pcount[(b + s) * kProtoCountStride + 2 * kProtoMaxActive + row];
-        t = warp_sum_i(t);
-        if (threadIdx.x == 0) a.tcnt[(int64_t)s * a.C + row] = t;
+    if (ky == 0 && a.first_pass) {
+        // ---- housekeeping of segment s (first pass only), spread over the column blocks ---------------
+        const uint32_t active_any = a.seg.mask_b[s];
+        // rows of classes that are not active on this client stay zero (proto = torch.zeros, :973): every column
+        // block clears its own 64 columns of those rows (16 rows x 16 float4 per sweep)
+        if (d < a.D) {
+            for (int row = grp; row < 2 * a.C; row += kFinGroups) {
+                if ((active_any >> (row >> 1)) & 1u) continue;
+                *reinterpret_cast<float4*>(a.proto + ((int64_t)s * 2 * a.C + row) * a.D + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (blockIdx.y == 0) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (threadIdx.x < 2 * a.C && !((active_any >> (threadIdx.x >> 1)) & 1u)) a.cnt[(int64_t)s * 2 * a.C + threadIdx.x] = 0;
+            // t counts: one warp per class adds the slots
+            if (a.tcnt != nullptr) {
+                for (int c = warp; c < a.C; c += 8) {
+                    int t = 0;
+                    if (a.has_t)
+                        for (int64_t b = b0 + lane; b <= b1; b += 32)
+                            t += a.pcount[(b + s) * kProtoCountStride + 2 * kProtoMaxActive + c];
+                    t = warp_sum_i(t);
+                    if (lane == 0) a.tcnt[(int64_t)s * a.C + c] = t;
+                }
+            }
+        }
     }
-    const int slot_i = __popc(pass_active & ((1u << c) - 1u));  // position among this pass's classes
+
+    // the slot_i-th class of this pass on this segment
+    uint32_t m = pass_active;
+    for (int i = 0; i < slot_i && m; ++i) m &= m - 1;
+    if (m == 0u) return;                                           // fewer active classes here than NA
+    const int c = __ffs(m) - 1;
+    const int row = 2 * c + y;
     // row count: the slots are independent loads -> spread them over the CTA, then add
     int n = 0;
-    if (mine)
-        for (int64_t b = b0 + threadIdx.x; b <= b1; b += blockDim.x) n += a.pcount[(b + s) * kProtoCountStride + 2 * slot_i + y];
+    for (int64_t b = b0 + threadIdx.x; b <= b1; b += blockDim.x) n += a.pcount[(b + s) * kProtoCountStride + 2 * slot_i + y];
     n = warp_sum_i(n);
     if ((threadIdx.x & 31) == 0) s_n[threadIdx.x >> 5] = n;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool col_ok = d < a.D;
-    if (mine && col_ok) {
+    if (col_ok) {
         const float* p0 = a.partial + ((int64_t)slot_i * 2 + y) * (int64_t)a.D + d;
         const int64_t slot_stride = (int64_t)a.NA * 2 * a.D;
         int64_t b = b0 + grp;
-        for (; b + 12 <= b1; b += 16) {
+        for (; b + 3 * kFinGroups <= b1; b += 4 * kFinGroups) {
             float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(p0 + (b + 4 * u + s) * slot_stride);
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(p0 + (b + kFinGroups * u + s) * slot_stride);
 #pragma unroll
             for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
-        for (; b <= b1; b += 4) {
+        for (; b <= b1; b += kFinGroups) {
             const float4 v = *reinterpret_cast<const float4*>(p0 + (b + s) * slot_stride);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
     }
-    s_part[grp][threadIdx.x & 63] = acc;
+    s_part[grp][cw] = acc;
     __syncthreads();
     n = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) n += s_n[w];
-    if (blockIdx.y == 0 && threadIdx.x == 0) {
-        if (mine) a.cnt[(int64_t)s * 2 * a.C + row] = n;
-        else if (a.first_pass && !active_any) a.cnt[(int64_t)s * 2 * a.C + row] = 0;
-    }
+    if (blockIdx.y == 0 && threadIdx.x == 0) a.cnt[(int64_t)s * 2 * a.C + row] = n;
     if (grp != 0 || !col_ok) return;
-    float4* out = reinterpret_cast<float4*>(a.proto + ((int64_t)s * 2 * a.C + row) * a.D + d);
-    if (!mine) {
-        // rows of classes that are not active on this client stay zero (proto = torch.zeros, :973)
-        if (a.first_pass && !active_any) *out = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
-    float4 t = s_part[0][threadIdx.x];
+    float4 t = s_part[0][cw];
 #pragma unroll
-    for (int g = 1; g < 4; ++g) {
-        const float4 v = s_part[g][threadIdx.x];
+    for (int g = 1; g < kFinGroups; ++g) {
+        const float4 v = s_part[g][cw];
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
     }
     if (!(n == 0 && a.guard_empty)) {
         const float fn = (float)n;
         t.x = __fdiv_rn(t.x, fn); t.y = __fdiv_rn(t.y, fn); t.z = __fdiv_rn(t.z, fn); t.w = __fdiv_rn(t.w, fn);
     }
-    *out = t;
+    *reinterpret_cast<float4*>(a.proto + ((int64_t)s * 2 * a.C + row) * a.D + d) = t;
 }
 
 template <int NA>
@@ -407,7 +429,7 @@ extern "C" int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, c
         rc = fill_seg_table(f.seg, S, seg_rows, pass, act_all);
         if (rc != FMLP_OK) return rc;
         f.D = D; f.C = C; f.NA = NA; f.guard_empty = guard_empty; f.first_pass = first ? 1 : 0; f.has_t = a.do_t;
-        dim3 fgrid((unsigned)(S * 2 * C), (unsigned)((D + 255) / 256));
+        dim3 fgrid((unsigned)(S * 2 * NA), (unsigned)((D + 4 * kFinCols - 1) / (4 * kFinCols)));
         {
             cudaLaunchConfig_t cfg = {};
             cudaLaunchAttribute attr[1];
