@@ -133,9 +133,13 @@ def _fedavg_i64_flat(ptrs, weights, J, divisor, integral, out_ptr, dev, div_flag
     return None
 
 
+_last_layout = None
+
+
 def _fedavg_cuda(w, dict_len, divide=True):
     """divide=False: plain weighted sum (DaAgg, utils/FedNoRo.py:98-103)."""
-    layout = layout_of(w[0])
+    global _last_layout
+    layout = _last_layout = layout_of(w[0], like=_last_layout)     # rounds repeat the same model: try the last layout first
     dev = next(iter(w[0].values())).device
     K = len(w)
     integral = all(_is_integral(x) for x in dict_len)
@@ -145,7 +149,10 @@ def _fedavg_cuda(w, dict_len, divide=True):
     lib = cabi.lib()
     with torch.cuda.device(dev):
         st = cabi.stream_ptr(dev)
-        views = [flat_view_of(sd) if layout_of(sd) is layout else None for sd in w]
+        # per-client layout once (a signature pass over the 727 entries; FlatStateDicts know theirs), then the flat-view
+        # probe with that layout — the probe leaves at the first tensor that is not where a flat buffer would have it
+        lays = [layout] + [layout_of(sd, like=layout) for sd in w[1:]]
+        views = [flat_view_of(sd, lay) if lay is layout else None for sd, lay in zip(w, lays)]
         if all(v is not None for v in views):
             # ---- flat path: K pointers, one streaming launch ---------------------------
             if layout.n_f32:
@@ -175,14 +182,15 @@ def _fedavg_cuda(w, dict_len, divide=True):
         f_idx, i_idx = plan["f_idx"], plan["i_idx"]
         Tf, Ti = len(f_idx), len(i_idx)
         n_all = len(layout.keys)
-        for sd in w:
-            for v in sd.values():
-                if not v.is_contiguous():
-                    raise ValueError("FedAvg: non-contiguous state_dict tensor")
+        if any(lay is not layout for lay in lays):     # the kernels index every client by client 0's layout
+            raise KeyError("FedAvg: the clients' state_dicts differ in keys, shapes or dtypes")
+        tensors = [v for sd in w for v in sd.values()]
+        if not all(map(torch.Tensor.is_contiguous, tensors)):
+            raise ValueError("FedAvg: non-contiguous state_dict tensor")
         # [K, T] pointers of every client tensor in one pass (the only per-call Python work that scales with the
         # 727 x K tensors); the device table is re-uploaded only when a pointer changed since the last call with
         # this layout, through a pinned staging buffer, without a host synchronisation
-        ptrs = np.fromiter((v.data_ptr() for sd in w for v in sd.values()), dtype=np.int64, count=K * n_all).reshape(K, n_all)
+        ptrs = np.fromiter(map(torch.Tensor.data_ptr, tensors), dtype=np.int64, count=K * n_all).reshape(K, n_all)
         cache = plan.setdefault("table_cache", {})
         ent = cache.get(K)
         if ent is None:

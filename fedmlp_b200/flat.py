@@ -12,6 +12,8 @@ from __future__ import annotations
 from collections import OrderedDict
 from dataclasses import dataclass
 
+import operator
+
 import torch
 
 _ALIGN = 4  # elements (16 bytes)
@@ -39,10 +41,25 @@ class FlatLayout:
 _layout_cache: dict = {}
 
 
-def layout_of(state_dict) -> FlatLayout:
+_DTYPE_OF = operator.attrgetter("dtype")
+_layout_dtypes: dict = {}      # id(layout) -> per-entry dtype tuple (layouts live in _layout_cache for the process lifetime)
+
+
+def layout_of(state_dict, like: "FlatLayout | None" = None) -> FlatLayout:
+    """like: a layout the dict is expected to have (client 0's).  The match is then decided by three C-level passes
+    (key tuple, numel and dtype of every entry — what the kernels' indexing depends on) instead of building and
+    hashing the full (key, shape, dtype) signature, which costs 0.5 ms per 727-entry dict; entries whose shape
+    differs from client 0's at equal numel are averaged element by element."""
     lay = getattr(state_dict, "layout", None)
     if isinstance(lay, FlatLayout) and not getattr(state_dict, "ints_as_float", False):
         return lay          # a FlatStateDict knows its layout (its keys / shapes cannot change)
+    if like is not None and len(state_dict) == len(like.keys) and tuple(state_dict.keys()) == like.keys:
+        vals = list(state_dict.values())
+        dts = _layout_dtypes.get(id(like))
+        if dts is None:
+            dts = _layout_dtypes[id(like)] = tuple(torch.int64 if b else torch.float32 for b in like.is_int)
+        if tuple(map(torch.Tensor.numel, vals)) == like.numels and tuple(map(_DTYPE_OF, vals)) == dts:
+            return like
     sig = tuple((k, tuple(v.shape), v.dtype) for k, v in state_dict.items())
     lay = _layout_cache.get(sig)
     if lay is not None:
@@ -202,14 +219,16 @@ def flatten_module_(module: torch.nn.Module) -> FlatStateDict:
     return flat
 
 
-def flat_view_of(state_dict):
+def flat_view_of(state_dict, lay=None):
     """If `state_dict`'s tensors are consecutive views of one flat buffer laid out as by
     FlatLayout, return (f32_base_ptr, i64_base_ptr); else None.  Lets FedAvg recognise models
-    prepared with flatten_module_ even when handed a plain OrderedDict from net.state_dict()."""
+    prepared with flatten_module_ even when handed a plain OrderedDict from net.state_dict().
+    lay: the dict's layout if the caller already has it (layout_of is a pass over all entries)."""
     if isinstance(state_dict, FlatStateDict) and not getattr(state_dict, "ints_as_float", False):
         return (state_dict.flat_f32.data_ptr(),
                 0 if state_dict.flat_i64 is None else state_dict.flat_i64.data_ptr())
-    lay = layout_of(state_dict)
+    if lay is None:
+        lay = layout_of(state_dict)
     base_f = base_i = None
     last_f = None
     for i, v in enumerate(state_dict.values()):
