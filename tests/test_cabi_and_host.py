@@ -158,3 +158,40 @@ def test_pool_layout_detection():
     assert pooling._layout_of(torch.zeros(3, 8, 49))[1:] == (pooling.FMAP_NCHW, 49)
     with pytest.raises(ValueError):
         pooling._layout_of(torch.zeros(3, 8))
+
+
+def test_tuning_knobs_and_new_entry_points_without_gpu(lib):
+    """fmlp_set_tuning / fmlp_get_tuning (scheduling knobs, include/fedmlp_b200.h) and the argument checks of the
+    round-2 aggregation-tails entry point: host-only behaviour, no CUDA call."""
+    from fedmlp_b200 import _cabi as c
+    for knob in (c.TUNE_PROTO_PAD_SMEM_KB, c.TUNE_SIM_REQUEST_SMEM_KB, c.TUNE_SIM_SMEM_BUDGET_KB, c.TUNE_SELECT_CLUSTER):
+        prev = lib.fmlp_get_tuning(knob)
+        assert lib.fmlp_set_tuning(knob, 8) == 0 and lib.fmlp_get_tuning(knob) == 8
+        assert lib.fmlp_set_tuning(knob, -1) == 0 and lib.fmlp_get_tuning(knob) == -1     # back to "unset"
+        assert lib.fmlp_set_tuning(knob, -2) == -1
+        lib.fmlp_set_tuning(knob, prev)
+    assert lib.fmlp_set_tuning(99, 1) == -1 and lib.fmlp_get_tuning(99) == -1
+    w = c.f64_array([1.0, 2.0])
+    masks = c.u64_array([1, 2, 3])
+    # null prototypes / zero total weight / counters without an output buffer
+    assert lib.fmlp_agg_tails_local_f32(None, 2, 3, 8, w, masks, 16, None, None, None, None, 0, 3.0, None, None, None) == -1
+    assert lib.fmlp_agg_tails_local_f32(16, 2, 3, 8, w, masks, 16, None, None, None, None, 0, 0.0, None, None, None) == -1
+    assert lib.fmlp_agg_tails_local_f32(16, 2, 3, 8, w, masks, 16, None, None, None, c.ptr_array([16, 16]), 4, 3.0, None, None, None) == -1
+    assert lib.fmlp_agg_tails_local_f32(16, 2, 3, 8, w, masks, 16, 16, None, None, None, 0, 3.0, 16, None, None) == -1   # tao needs rows / masks
+
+
+def test_fast_layout_match_is_strict_about_sizes_and_dtypes():
+    """flat.layout_of(sd, like=...) (the per-client layout check of FedAvg on scattered state_dicts) accepts only dicts
+    whose keys, element counts and dtypes equal client 0's."""
+    from collections import OrderedDict
+
+    import torch
+
+    from fedmlp_b200.flat import layout_of
+    a = OrderedDict(w=torch.zeros(3, 4), b=torch.zeros(4), n=torch.zeros((), dtype=torch.int64))
+    lay = layout_of(a)
+    same = OrderedDict(w=torch.ones(3, 4), b=torch.ones(4), n=torch.ones((), dtype=torch.int64))
+    assert layout_of(same, like=lay) is lay
+    assert layout_of(OrderedDict(w=torch.ones(3, 5), b=torch.ones(4), n=torch.ones((), dtype=torch.int64)), like=lay) is not lay
+    assert layout_of(OrderedDict(w=torch.ones(3, 4), c=torch.ones(4), n=torch.ones((), dtype=torch.int64)), like=lay) is not lay
+    assert layout_of(OrderedDict(w=torch.ones(3, 4), b=torch.ones(4, dtype=torch.int64), n=torch.ones((), dtype=torch.int64)), like=lay) is not lay
