@@ -39,6 +39,7 @@ _sz = C.c_size_t
 # name -> (restype, argtypes); mirrors include/fedmlp_b200.h one to one
 SIGNATURES = {
     "fmlp_abi_version": (_i, []),
+    "fmlp_host_copy_many": (_i, [_p, _p, _p, C.c_int64, _i]),
     "fmlp_set_tuning": (_i, [_i, _i]),
     "fmlp_get_tuning": (_i, [_i]),
     "fmlp_status_string": (C.c_char_p, [_i]),

@@ -1,4 +1,8 @@
 // cabi.cu — ABI version / status strings / device queries of libfedmlp_b200.
+#include <cstring>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace fmlp {
@@ -32,4 +36,39 @@ extern "C" int fmlp_set_tuning(int knob, int value) {
 extern "C" int fmlp_get_tuning(int knob) {
     if (knob < 0 || knob >= FMLP_TUNE_COUNT) return -1;
     return __atomic_load_n(&fmlp::g_tuning[knob], __ATOMIC_RELAXED);
+}
+
+// Host utility: n independent memcpy's (dsts[i] <- srcs[i], nbytes[i] bytes), split over `n_threads` host threads by
+// bytes.  Used by FedAvg's CPU-state_dict path to pack 727 pageable tensors per client into one pinned buffer at
+// memory bandwidth (a per-tensor torch copy costs ~7 us of dispatch each: 62 ms for 8 DenseNet121 clients).
+extern "C" int fmlp_host_copy_many(const void* const* srcs, void* const* dsts, const int64_t* nbytes, int64_t n, int n_threads) {
+    if (n < 0 || (n > 0 && (!srcs || !dsts || !nbytes))) return FMLP_ERR_BAD_ARG;
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (nbytes[i] < 0 || (nbytes[i] > 0 && (!srcs[i] || !dsts[i]))) return FMLP_ERR_BAD_ARG;
+        total += nbytes[i];
+    }
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (total < (int64_t)1 << 20 || n_threads == 1) {
+        for (int64_t i = 0; i < n; ++i) if (nbytes[i]) memcpy(dsts[i], srcs[i], (size_t)nbytes[i]);
+        return FMLP_OK;
+    }
+    // byte ranges [t*share, (t+1)*share) of the concatenated copy list; a tensor may be split between two threads
+    const int64_t share = (total + n_threads - 1) / n_threads;
+    auto work = [&](int t) {
+        const int64_t lo = (int64_t)t * share, hi = lo + share < total ? lo + share : total;
+        int64_t pos = 0;
+        for (int64_t i = 0; i < n && pos < hi; ++i) {
+            const int64_t b = nbytes[i], a0 = pos > lo ? pos : lo, a1 = pos + b < hi ? pos + b : hi;
+            if (a1 > a0) memcpy((char*)dsts[i] + (a0 - pos), (const char*)srcs[i] + (a0 - pos), (size_t)(a1 - a0));
+            pos += b;
+        }
+    };
+    std::vector<std::thread> th;
+    th.reserve(n_threads - 1);
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    return FMLP_OK;
 }

@@ -233,29 +233,53 @@ def _fedavg_cuda(w, dict_len, divide=True):
 _pinned_pool: dict = {}
 
 
-def _stage_cpu_client(sd, dev, slot=0):
-    """Pack a CPU state_dict into pinned flat buffers (one foreach copy) and upload them.  The pinned buffers
-    are pooled per (layout, client slot): cudaHostAlloc of 28 MB costs milliseconds, and FedAvg's CPU path ends
-    with a device-to-host read that synchronises, so a slot is free again when the next call starts."""
-    lay = layout_of(sd)
+def _pinned_entry(lay, slot):
+    """Pinned flat staging buffers of one client slot plus the per-tensor destination pointers / byte counts of the
+    layout, pooled per (layout, slot): cudaHostAlloc of 28 MB costs milliseconds, and FedAvg's CPU path ends with a
+    device-to-host read that synchronises, so a slot is free again when the next call starts."""
     key = (lay, slot)
-    bufs = _pinned_pool.get(key)
-    if bufs is None:
-        bufs = _pinned_pool[key] = (torch.zeros(max(lay.n_f32, 1), dtype=torch.float32, pin_memory=True),
-                                    torch.zeros(max(lay.n_i64, 1), dtype=torch.int64, pin_memory=True))
-    pin_f, pin_i = bufs
-    views = []
-    for i in range(len(lay.keys)):
-        n, off = lay.numels[i], lay.offsets[i]
-        buf = pin_i if lay.is_int[i] else pin_f
-        views.append(buf[off:off + n].view(lay.shapes[i]))
-    torch._foreach_copy_(views, [v.detach() for v in sd.values()])
-    d = FlatStateDict.empty(lay, dev)
-    if lay.n_f32:
-        d.flat_f32.copy_(pin_f[:lay.n_f32], non_blocking=True)
-    if d.flat_i64 is not None:
-        d.flat_i64.copy_(pin_i[:lay.n_i64], non_blocking=True)
-    return d
+    ent = _pinned_pool.get(key)
+    if ent is None:
+        pin_f = torch.zeros(max(lay.n_f32, 1), dtype=torch.float32, pin_memory=True)
+        pin_i = torch.zeros(max(lay.n_i64, 1), dtype=torch.int64, pin_memory=True)
+        is_int = np.array(lay.is_int, dtype=bool)
+        offs = np.array(lay.offsets, dtype=np.int64)
+        numels = np.array(lay.numels, dtype=np.int64)
+        dsts = np.where(is_int, pin_i.data_ptr() + 8 * offs, pin_f.data_ptr() + 4 * offs).astype(np.int64)
+        nbytes = np.where(is_int, 8 * numels, 4 * numels).astype(np.int64)
+        ent = _pinned_pool[key] = (pin_f, pin_i, np.ascontiguousarray(dsts), np.ascontiguousarray(nbytes))
+    return ent
+
+
+def _stage_cpu_clients(w, dev):
+    """Pack K CPU state_dicts into pinned flat buffers and upload them.  Per client: one pass for the 727 source
+    pointers, ONE call of fmlp_host_copy_many (host threads, memory bandwidth) into the pooled pinned buffer, one
+    asynchronous upload — the packing of client i+1 overlaps the upload of client i.  (Packing with per-tensor torch
+    copies cost ~7 us of dispatch per tensor: 62 ms for 8 DenseNet121 clients, no faster than the reference's CPU
+    FedAvg.)"""
+    global _last_layout
+    import os
+    lib = cabi.lib()
+    n_threads = max(1, min(16, (os.cpu_count() or 1)))
+    staged = []
+    for i, sd in enumerate(w):
+        lay = _last_layout = layout_of(sd, like=_last_layout)
+        pin_f, pin_i, dsts, nbytes = _pinned_entry(lay, i)
+        vals = list(sd.values())
+        if not all(map(torch.Tensor.is_contiguous, vals)):
+            raise ValueError("FedAvg: non-contiguous state_dict tensor")
+        if any(v.is_cuda for v in vals):
+            raise TypeError("FedAvg: a state_dict mixes CPU and CUDA tensors")
+        srcs = np.fromiter(map(torch.Tensor.data_ptr, vals), dtype=np.int64, count=len(vals))
+        cabi.check(lib.fmlp_host_copy_many(srcs.ctypes.data, dsts.ctypes.data, nbytes.ctypes.data, len(vals), n_threads),
+                   "fmlp_host_copy_many")
+        d = FlatStateDict.empty(lay, dev, lazy=True, zero=False)      # only the flat buffers are used
+        if lay.n_f32:
+            d.flat_f32.copy_(pin_f[:lay.n_f32], non_blocking=True)
+        if d.flat_i64 is not None:
+            d.flat_i64.copy_(pin_i[:lay.n_i64], non_blocking=True)
+        staged.append(d)
+    return staged
 
 
 def FedAvg(w, dict_len, _divide=True):
@@ -278,7 +302,7 @@ def FedAvg(w, dict_len, _divide=True):
     if not torch.cuda.is_available():
         raise cabi.FedMLPNativeError("FedAvg needs a CUDA device (fedmlp_b200 has no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
-    staged = [_stage_cpu_client(sd, dev, slot=i) for i, sd in enumerate(w)]
+    staged = _stage_cpu_clients(w, dev)
     res = _fedavg_cuda(staged, dict_len, _divide)
     host_flat = res.flat_f32.cpu()
     out = OrderedDict()

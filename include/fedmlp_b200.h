@@ -55,6 +55,11 @@ int fmlp_sm_count(void);
 /* Kernel launches issued by this library since it was loaded (process-wide, monotonic). */
 unsigned long long fmlp_launch_count(void);
 
+/* Host utility (no CUDA call): n independent copies dsts[i] <- srcs[i] of nbytes[i] bytes, split over n_threads host
+ * threads by bytes.  FedAvg's CPU-state_dict path (the reference hands over `net.cpu()` weights in stage 2,
+ * utils/local_training.py:1251, main.py:196) packs a client's 727 pageable tensors into one pinned buffer with it. */
+int fmlp_host_copy_many(const void* const* srcs, void* const* dsts, const int64_t* nbytes, int64_t n, int n_threads);
+
 /* Scheduling knobs for rounds that run several of these kernels concurrently on different streams (process-wide;
  * value -1 = unset: the environment variable of the same meaning, then the built-in default, applies).
  *   FMLP_TUNE_PROTO_PAD_SMEM_KB   unused dynamic shared memory requested per prototype-accumulate CTA (0..56 KB):

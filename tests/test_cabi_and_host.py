@@ -195,3 +195,23 @@ def test_fast_layout_match_is_strict_about_sizes_and_dtypes():
     assert layout_of(OrderedDict(w=torch.ones(3, 5), b=torch.ones(4), n=torch.ones((), dtype=torch.int64)), like=lay) is not lay
     assert layout_of(OrderedDict(w=torch.ones(3, 4), c=torch.ones(4), n=torch.ones((), dtype=torch.int64)), like=lay) is not lay
     assert layout_of(OrderedDict(w=torch.ones(3, 4), b=torch.ones(4, dtype=torch.int64), n=torch.ones((), dtype=torch.int64)), like=lay) is not lay
+
+
+def test_host_copy_many_packs_exactly(lib):
+    """fmlp_host_copy_many (host threads): byte-exact copies incl. tensors split between two threads, empty entries."""
+    import numpy as np
+    import torch
+    g = torch.Generator().manual_seed(5)
+    sizes = [0, 1, 7, 300_000, 5, 900_001, 64, 0, 123_457]
+    srcs = [torch.randn(n, generator=g) for n in sizes]
+    dst = torch.full((sum(sizes) + 16,), -7.0)
+    offs = np.cumsum([0] + sizes[:-1]).astype(np.int64)
+    sp = np.array([s.data_ptr() if s.numel() else 0 for s in srcs], dtype=np.int64)
+    dp = np.ascontiguousarray(dst.data_ptr() + 4 * offs)
+    nb = np.array([4 * n for n in sizes], dtype=np.int64)
+    for threads in (1, 3, 8):
+        dst.fill_(-7.0)
+        assert lib.fmlp_host_copy_many(sp.ctypes.data, dp.ctypes.data, nb.ctypes.data, len(sizes), threads) == 0
+        assert torch.equal(dst[:sum(sizes)], torch.cat(srcs))
+        assert bool((dst[sum(sizes):] == -7.0).all())
+    assert lib.fmlp_host_copy_many(None, None, None, 2, 1) == -1
