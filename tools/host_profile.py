@@ -9,9 +9,10 @@ from fedmlp_b200 import _cabi as cabi
 
 a = bench.parse_args()
 dev = torch.device("cuda", 0)
-inp = bench.make_device_inputs(a, 0, dev)
-S, C = a.clients_per_gpu, a.classes
-shard = ClientShard([a.rows_per_client] * S, C, [[k % C] for k in range(S)], device=dev)
+w = bench.Workload(a.config, a)
+inp = bench.make_device_inputs(w, 0, dev)
+S, C = w.S, w.C
+shard = ClientShard([w.n] * S, C, [[k % C] for k in range(S)], device=dev)
 fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
 def step():
     return shard.round_hot_path(inp["feat_tag"], inp["proto"], inp["logits"], inp["logits_glob"], inp["labels"],
