@@ -536,7 +536,9 @@ extern "C" int fmlp_fill_loss_stage2_f32(const float* labels, const uint8_t* tag
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
     const int64_t tile = (int64_t)kLossThreads * kLossUnroll;
     int64_t grid = (n_el + tile - 1) / tile;
-    if (grid > 2 * (int64_t)sms) grid = 2 * (int64_t)sms;        // two CTAs per SM: latency-bound element-wise work
+    // one 1024-element tile per CTA while all CTAs are co-resident (8 x 256 threads per SM): every extra tile per CTA
+    // is another dependent round of L2 latency in a latency-bound kernel (r02: 2 CTAs per SM meant 3 rounds at C = 14)
+    if (grid > 8 * (int64_t)sms) grid = 8 * (int64_t)sms;
     if (grid > kLossMaxGrid - FMLP_MAX_SEGMENTS) grid = kLossMaxGrid - FMLP_MAX_SEGMENTS;  // slots b + s
     if (grid < 1) grid = 1;
     int64_t epc = (n_el + grid - 1) / grid;
