@@ -270,8 +270,12 @@ int fmlp_proto_build_f32(const float* feat, int64_t ld_feat, int D, const float*
  *           (half the FMAs; differs from PAIR by O(1e-7), inside the north_star waiver)
  *   ws      fmlp_tag_sim_ws_bytes(C, D) bytes, 16-byte aligned: the class-vector table a small
  *           pre-kernel builds once per call (prototype norms, folded vectors) and every CTA of
- *           the streaming kernel copies; the two launches are chained by a programmatic
- *           dependent launch                                                                */
+ *           the streaming kernel copies; the two launches are chained by programmatic
+ *           dependent launches (the pre-kernel to whatever precedes it in the stream, the
+ *           streaming kernel to the pre-kernel; every global read sits behind a
+ *           griddepcontrol.wait, so the call is stream-ordered like any other)
+ * The streaming kernel is persistent (one CTA per SM: 8 compute warps fed by 2-D TMA boxes +
+ * 2 epilogue warps) and takes 160-227 KB of shared memory per CTA.                           */
 enum { FMLP_SIM_PAIR = 0, FMLP_SIM_FOLDED = 1 };
 size_t fmlp_tag_sim_ws_bytes(int C, int D);
 int fmlp_tag_sim_f32(const float* feat, int64_t ld_feat, int D, const float* proto, int C,
@@ -317,7 +321,11 @@ int fmlp_pool_tag_f32(const float* fmap, int layout, int B, int D, int HW, int r
  *             selection = the number of `distill` entries of that (client, class), :1467-1468
  *   sel       [S, C, 2, cap] int32 out: global row numbers, side 0 = clean, 1 = noise
  *   cap       per-(segment,class,side) capacity; must be >= the largest possible m or k
- * ws: fmlp_tag_select_ws_bytes(S, C, cap).                                                */
+ * ws: fmlp_tag_select_ws_bytes(S, C, cap).
+ * Launch shape: one 1024-thread CTA per (segment, class) item while the largest segment has at most 16,384 rows
+ * (keys in registers); beyond that one thread-block cluster of 2 / 4 / 8 CTAs per item (histograms merged through
+ * distributed shared memory).  FMLP_TUNE_SELECT_CLUSTER forces the split.  Programmatic dependent launch behind
+ * the preceding kernel of the stream (all reads sit behind griddepcontrol.wait).                */
 size_t fmlp_tag_select_ws_bytes(int S, int C, int64_t cap);
 int fmlp_tag_select(const float* sim, int64_t ld_sim, uint8_t* tag, int64_t ld_tag, int C,
                     int S, const int64_t* seg_rows, const uint32_t* seg_missing,
