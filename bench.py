@@ -369,7 +369,12 @@ class Runner:
         self.shard.keep_history = False      # host-list bookkeeping (two small device clones per round) is off the timed path
         self.shard.loss_variant = cabi.LOSS2_SUP_DIS if w.loss == "sup_dis" else cabi.LOSS2_SUP
         self.fed_out = torch.empty(inp["Ppad"], dtype=torch.float32, device=dev)
-        self.side_stream = torch.cuda.Stream(device=dev)
+        # FMLP_MAIN_PRIORITY / FMLP_SIDE_PRIORITY: CUDA stream priorities of the tagging / loss chain (the stream the round's
+        # graph is captured on) and of the prototype / aggregation chain (0 = default, -1 .. = higher); measured on one
+        # GPU: a higher side priority costs 8 % (profiles/r02_exp_coresidency.txt)
+        mp = int(os.environ.get("FMLP_MAIN_PRIORITY", "0"))
+        self.capture_stream = torch.cuda.Stream(device=dev, priority=mp) if mp != 0 else None
+        self.side_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("FMLP_SIDE_PRIORITY", "0")))
         n_streams = a.streams or (2 if world == 1 else 3)
         # the parameter exchange gets a HIGH-priority stream: its (persistent, small-footprint) CTAs must be placed
         # before the prototype / similarity kernels of the other streams fill every SM's register file
@@ -537,7 +542,7 @@ class Runner:
                         self.shard.schedule = sched
                     l0 = lib.fmlp_launch_count()
                     g_ = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g_):
+                    with torch.cuda.graph(g_, stream=self.capture_stream):
                         self.step()
                     n_launch = lib.fmlp_launch_count() - l0
                     t_ms = None
