@@ -215,3 +215,28 @@ def test_host_copy_many_packs_exactly(lib):
         assert torch.equal(dst[:sum(sizes)], torch.cat(srcs))
         assert bool((dst[sum(sizes):] == -7.0).all())
     assert lib.fmlp_host_copy_many(None, None, None, 2, 1) == -1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver launches beside the GPU arm): one JSON line on stdout with the
+    GPU arm's metric / unit / config keys, impl = reference, an e2e block of its own value and zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--rows-per-client", "200",
+                          "--clients-per-gpu", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=300, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "client_samples_per_sec_per_fedmlp_round" and d["unit"] == "client-samples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    import bench
+    keys = set(bench.Workload("ich55k").config_keys(1))
+    assert keys <= set(d["config"]), "the reference arm must print the GPU arm's config keys"
