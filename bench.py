@@ -103,6 +103,25 @@ class Workload:
         return {"workload": self.description(), "name": self.name, "clients_per_gpu": self.S, "rows_per_client": self.n,
                 "feature_dim": self.D, "classes": self.C, "backbone": self.backbone, "params_per_client": P}
 
+    def full_config(self, a, world):
+        """The `config` object of the JSON line — the SAME for the GPU arm and the reference arm of one (workload, N,
+        flags), computed from shapes alone (no device): workload keys + how L2 is kept out of the measurement +
+        how the clients are spread over the GPUs."""
+        import torch
+        from fedmlp_b200.shapes import count_params
+        shapes = self.state_shapes()
+        P = count_params(shapes)[0]
+        Ppad = sum((int(torch.Size(sh).numel()) + 3) // 4 * 4 for sh, dt in shapes.values() if dt == torch.float32)
+        ab = alg_bytes(self, {"N": self.S * self.n, "Ppad": Ppad})
+        total = ab["sim"] + ab["proto"] + ab["fedavg"] + ab["loss"] + ab["select_fill"]
+        cfg = self.config_keys(P)
+        cfg.update({"sim_mode": a.sim_mode,
+                    "l2": f"inputs larger than L2: {round(total / 1e6)} MB streamed per step vs 126 MB L2, no flush needed",
+                    "parallelism": (f"clients sharded over {world} GPU(s), one process per GPU; only the aggregation crosses GPUs, on "
+                                    "its own streams, concurrent with the tagging/loss chain") if world > 1 else "single GPU",
+                    "not_in_timed_step": "host-list bookkeeping of traindata_idx (two small device clones per round, keep_history)"})
+        return cfg
+
     def state_shapes(self):
         from fedmlp_b200.shapes import densenet121_state_shapes, efficientnet_b0_state_shapes
         return densenet121_state_shapes(self.C) if self.backbone == "DenseNet121" else efficientnet_b0_state_shapes(self.C)
@@ -295,7 +314,7 @@ def reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": w.config_keys(r["P"]),
+        "config": w.full_config(a, a.gpus),
         "steps_executed": r["steps_executed"],
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "fedavg_gbs": (w.S + 1) * 4 * r["P"] / r["t_fedavg"] / 1e9,
@@ -826,24 +845,11 @@ def gpu_arm(a):
             r = run_cpu_arm(w, steps=5, warmup=1, n_clients=a.cpu_clients, budget_s=30.0)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                    "ms_per_step": r["t_step"] * 1e3, "fedavg_gbs": (w.S + 1) * 4 * r["P"] / r["t_fedavg"] / 1e9}
-        shapes_P = None
-        try:
-            from fedmlp_b200.shapes import count_params
-            shapes_P = count_params(w.state_shapes())[0]
-        except Exception:
-            pass
-        cfg = w.config_keys(shapes_P)
-        ab_total = headline["step_alg_bytes"]
-        cfg.update({"sim_mode": a.sim_mode,
-                    "l2": f"inputs larger than L2: {round(ab_total / 1e6)} MB streamed per step vs 126 MB L2, no flush needed",
-                    "parallelism": (f"clients sharded over {world} GPU(s), one process per GPU; only the aggregation crosses GPUs, on a "
-                                    "side stream with the prototype pass, concurrent with the tagging/loss chain") if world > 1 else "single GPU",
-                    "collective": headline_collective,
-                    "not_in_timed_step": "host-list bookkeeping of traindata_idx (two small device clones per round, keep_history)"})
+        cfg = w.full_config(a, world)      # identical to the reference arm's `config` for the same workload, N and flags
         line = {
             "metric": METRIC, "value": headline["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": headline["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": cfg,
+            "data": "synthetic", "config": cfg, "collective": headline_collective,
             "fedavg_gbs": headline["kernels"]["fedavg"].get("gbs"),
             "roofline": headline["roofline"], "kernels": headline["kernels"], "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": headline["launches"], "gpu_launches_per_step": headline["launches_per_step"], "clocks": clocks,

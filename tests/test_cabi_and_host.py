@@ -238,5 +238,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     import bench
-    keys = set(bench.Workload("ich55k").config_keys(1))
-    assert keys <= set(d["config"]), "the reference arm must print the GPU arm's config keys"
+    a = bench.parse_args.__globals__["argparse"].Namespace(sim_mode="folded", clients_per_gpu=2, rows_per_client=200)
+    # the GPU arm builds its `config` with the same call: equal objects for the same workload, N and flags
+    assert d["config"] == bench.Workload("ich55k", a).full_config(a, 1)
+    assert "l2" in d["config"] and "workload" in d["config"] and "collective" not in d["config"]

@@ -5,4 +5,4 @@ mkdir -p gpurun_out
 echo "rc=$?"; tail -3 gpurun_out/bench_r02_8gpu.err
 python tools/show_bench.py gpurun_out/bench_r02_8gpu.json | grep -v loss_sweep
 python -c "
-import json; d=json.loads(open('gpurun_out/bench_r02_8gpu.json').read().strip().splitlines()[-1]); print(d['config']['collective'][:200]); print([ (c['name'], c['parity']['parity_ok']) for c in d['configs']])"
+import json; d=json.loads(open('gpurun_out/bench_r02_8gpu.json').read().strip().splitlines()[-1]); print(d['collective'][:200]); print([ (c['name'], c['parity']['parity_ok']) for c in d['configs']])"

@@ -14,6 +14,6 @@ import json,glob
 for f in sorted(glob.glob('gpurun_out/bench_r02_2gpu_*.json')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, round(d['ms_per_step'],4), {k:v.get('ms') for k,v in d['kernels'].items()}, d.get('parity_ok'), (d.get('e2e') or {}).get('ms_per_step'), d['config']['collective'][:60])
+        print(f, round(d['ms_per_step'],4), {k:v.get('ms') for k,v in d['kernels'].items()}, d.get('parity_ok'), (d.get('e2e') or {}).get('ms_per_step'), d['collective'][:60])
     except Exception as e: print(f, 'ERR', e)
 PY
