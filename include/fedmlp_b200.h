@@ -4,7 +4,7 @@
  * Drop-in boundary for the FedMLP per-round hot path (tag + prototypes + loss + FedAvg) on
  * NVIDIA B200 (sm_100a).  The reference (szbonaldo/FedMLP) is pure Python/PyTorch and has no
  * FFI of its own; every entry point below therefore cites the reference
- * *Python* block it replaces.  Host code (fedmlp_b200/*.py, ctypes) keeps the reference's call
+ * *Python* block it replaces.  Host code (the fedmlp_b200 package, ctypes) keeps the reference's call
  * surface and forwards raw device pointers + the caller's CUDA stream to these functions.
  *
  * Conventions (all entry points):
