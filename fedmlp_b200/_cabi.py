@@ -14,7 +14,7 @@ import os as _os
 # FEDMLP_B200_LIB: alternative build of the same library (tuning experiments under tools/); the default is in-tree
 LIB_PATH = Path(_os.environ.get("FEDMLP_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libfedmlp_b200.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TUNE_PROTO_PAD_SMEM_KB, TUNE_SIM_REQUEST_SMEM_KB, TUNE_SIM_SMEM_BUDGET_KB, TUNE_SELECT_CLUSTER = 0, 1, 2, 3
 MAX_CLASSES = 32
 MAX_SEGMENTS = 64

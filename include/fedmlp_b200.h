@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FMLP_ABI_VERSION 3 /* 3: fmlp_tag_sim_f32 takes a workspace (class-vector table); 2: allreduce n_chunks, pool_tag, eval, adam */
+#define FMLP_ABI_VERSION 4 /* 4: + fmlp_agg_tails_local_f32, fmlp_set/get_tuning, fmlp_host_copy_many; 3: fmlp_tag_sim_f32 takes a workspace (class-vector table); 2: allreduce n_chunks, pool_tag, eval, adam */
 #define FMLP_MAX_CLASSES 32   /* class bit masks are uint32_t                        */
 #define FMLP_MAX_SEGMENTS 64  /* segments (clients) per launch                        */
 #define FMLP_MAX_CLIENTS 64   /* client buffers folded per fedavg launch              */
